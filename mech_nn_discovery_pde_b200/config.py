@@ -1,0 +1,33 @@
+"""Solver knobs of the PDE layer.  Attribute names mirror the reference's ``config.PDEConfig``
+(config.py:13-29) and are read at call time, so assigning to the class attributes (as the reference's
+notebooks do) changes the next forward/backward call."""
+
+
+class PDEConfig:
+    # multigrid options (config.py:13-26)
+    mg_gauss_seidel_steps_pre = 5
+    mg_gauss_seidel_steps_post = 5
+
+    mg_steps_forward = 1
+    mg_steps_backward = 1
+
+    mg_fgmres_max_iter_forward = 40
+    mg_fgmres_restarts_forward = 10
+
+    mg_fgmres_max_iter_backward = 40
+    mg_fgmres_restarts_backward = 10
+
+    # accepted for compatibility; the reference never reads it on the live path (config.py:29)
+    jacobi_w = 0.4
+
+    # --- additions of this implementation -------------------------------------------------------
+    # absolute tolerance on the batch-global residual (fgmres.py:22, atol=1e-5)
+    mg_fgmres_atol = 1e-5
+    # The reference's add_pad allocates its buffer with the default dtype, so d(loss)/d(rhs) is rounded
+    # to fp32 even on the fp64 path (lp_pde_central_diff.py:1634).  False: keep fp64 (default).
+    rhs_grad_fp32_quirk = False
+    # Read the Cholesky status back after each forward and raise torch.linalg.LinAlgError like
+    # cholesky_ex(check_errors=True) (multigrid.py:439).  Costs one host sync per forward.
+    check_factorization = True
+    # 0: production wavefront Gauss-Seidel kernel; 1: one launch per hyperplane (debug cross-check)
+    gs_variant = 0

@@ -1,0 +1,56 @@
+// pdeop -- backend interface between the host-side orchestration (pdeop_solver.cpp) and the kernels.
+// The product implements it with CUDA kernels for sm_100a (pdeop_cuda.cu).  tests/emu implements it
+// with plain loops over the same per-element bodies so the orchestration and index algebra can be
+// checked on a machine without a GPU; that emulator is test infrastructure and is never loaded by
+// the product package.
+#pragma once
+#include <stddef.h>
+#include "pdeop_common.h"
+
+namespace pdeop {
+
+typedef void* stream_t;  // cudaStream_t in the CUDA build
+
+const char* be_name();
+void* be_alloc(size_t bytes);
+void be_free(void* p);
+void be_upload(void* dst, const void* src, size_t bytes);
+void be_zero(stream_t st, void* p, size_t bytes);
+int be_last_error(char* buf, int len);  // 0 if no pending error
+
+void be_build_tables(stream_t st, const LevelDev& L, int B, const double* cv, const double* fv, const double* bv,
+                     double* T);
+void be_pack(stream_t st, const LevelDev& L, int B, const double* api, double* wave);
+void be_unpack(stream_t st, const LevelDev& L, int B, const double* wave, double* api);
+void be_interp(stream_t st, const LevelDev& Li, const LevelDev& Lo, int B, int C, const double* in, double* out,
+               int add, const int* done);
+void be_atb(stream_t st, const LevelDev& L, int B, const double* coef, const double* rhs_nat, const double* iv_rhs,
+            double* atb);
+// y = K x (mode 0) or y = b - K x (mode 1)
+void be_apply_k(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, const double* x,
+                const double* b, double* y, int mode, const int* done);
+// nsweeps lexicographic Gauss-Seidel sweeps, in place.  variant 0: production kernel; 1: one launch per
+// hyperplane step (test cross-check).
+void be_gs(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, const double* b, double* x,
+           int nsweeps, const int* done, int variant);
+void be_dense(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, double* Kd);
+// in-place lower Cholesky of B dense n x n matrices; state->chol_info set on a non-positive pivot
+void be_cholesky(stream_t st, int B, int n, double* Kd, FgmresState* state);
+// out = (L L^T)^-1 rhs
+void be_chol_solve(stream_t st, int B, int n, const double* Lf, const double* rhs, double* out, double* work,
+                   const int* done);
+void be_grads(stream_t st, const LevelDev& L, int B, const double* coef, const double* rhs_nat, const double* cv,
+              const double* fv, const double* bv, const double* x, const double* dz, double* d_coeffs,
+              double* d_rhs, double* d_iv, double* d_cv, double* d_fv, double* d_bv);
+
+// FGMRES vector steps on flat vectors of length n (whole local batch: global norms, fgmres.py:76,128,158)
+void be_fg_begin(stream_t st, size_t n, const double* b, double* x, FgmresState* s);
+void be_fg_resnorm(stream_t st, size_t n, const double* r, FgmresState* s, int maxiter, double atol);
+void be_fg_first(stream_t st, size_t n, const double* r, double* V0, FgmresState* s);
+void be_fg_cgs(stream_t st, size_t n, int j, int restart, double* V, double* w, FgmresState* s);
+void be_fg_update(stream_t st, size_t n, int restart, const double* Z, double* x, FgmresState* s);
+void be_fg_info(stream_t st, const FgmresState* s, double* info4);
+void be_fg_hess(stream_t st, const FgmresState* s, int restart, double* hess_out);
+void be_state_reset(stream_t st, FgmresState* s);
+
+}  // namespace pdeop

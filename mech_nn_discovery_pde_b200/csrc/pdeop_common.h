@@ -1,0 +1,80 @@
+// pdeop -- B200-native differentiable PDE-layer solve.  Shared definitions.
+//
+// Internal data model:
+//  * Every grid is embedded in 3 internal axes (N0,N1,N2); a d-dimensional problem uses the last d
+//    axes ("active" axes), leading axes have extent 1.
+//  * Grid points are stored in WAVE ORDER: sorted by hyperplane s=i0+i1+i2, then (i0,i1).  Points of
+//    one hyperplane are independent under lexicographic Gauss-Seidel (the normal operator couples
+//    points only along grid axes), so a hyperplane is a contiguous, coalesced index range.
+//  * Vectors are channel-planar: v[b][m][w], m in [0,M), M=1+2d channels (u, u_c, u_cc), w wave index.
+//  * The constraint matrix A is never formed.  Per instance and axis a small table T holds the
+//    axis part of K=A^T A per line position (30 numbers), built from the per-line row values.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PDEOP_HD __host__ __device__ __forceinline__
+#else
+#define PDEOP_HD inline
+#endif
+
+namespace pdeop {
+
+constexpr int kTabEntries = 30;   // Cuu[9] | Cup[9] | Cuq[9] | pp | qq | pq
+constexpr int kTabPad = 4;        // stencil radius of K along an axis
+constexpr int kGsLag = 5;         // hyperplane lag between pipelined Gauss-Seidel sweeps (radius + 1)
+constexpr int kMaxRestart = 32;
+
+enum TabIdx { T_UU = 0, T_UP = 9, T_UQ = 18, T_PP = 27, T_QQ = 28, T_PQ = 29 };
+
+// Immutable per-level index tables (device pointers in the CUDA build, host pointers in the emulator).
+struct LevelDev {
+    int N[3];        // internal extents
+    int D;           // active axes (problem dimension); active internal axes are 3-D .. 2
+    int M;           // channels = 1 + 2*D
+    int G;           // grid points
+    int S;           // hyperplanes = N0+N1+N2-2
+    int P;           // table pitch = max(N)+8
+    int n_init;      // initial/boundary rows
+    int n_eq;        // equation rows
+    int Ntot;        // sum of active extents          (central row-value table length)
+    int Ftot;        // sum of (active extents - 1)    (forward/backward row-value table length)
+    int cvoff[3];    // per active axis a: offset into the central line table
+    int fvoff[3];    // per active axis a: offset into the forward/backward line tables
+    const int* coord;    // [G]  i0 | i1<<10 | i2<<20, wave order
+    const int* flags;    // [G]  bit0: carries an equation row; bits 4+2m..5+2m: # initial rows on channel m
+    const int* hstart;   // [S+1] first wave index of each hyperplane
+    const int* rowbase;  // [(S+8)*N0] pos(i0,i1,i2) = rowbase[(s+4)*N0+i0] + i1
+    const int* init_w;   // [n_init] wave index of each initial row's variable
+    const int* init_m;   // [n_init] channel of each initial row's variable
+};
+
+PDEOP_HD void unpack_coord(int c, int& i0, int& i1, int& i2) {
+    i0 = c & 1023;
+    i1 = (c >> 10) & 1023;
+    i2 = (c >> 20) & 1023;
+}
+
+PDEOP_HD int wave_pos(const LevelDev& L, int i0, int i1, int i2) {
+    return L.rowbase[(i0 + i1 + i2 + 4) * L.N[0] + i0] + i1;
+}
+
+PDEOP_HD int nat_index(const LevelDev& L, int i0, int i1, int i2) {
+    return (i0 * L.N[1] + i1) * L.N[2] + i2;
+}
+
+// Device-resident FGMRES bookkeeping: nothing here is read by the host inside a solve.
+struct FgmresState {
+    double H[(kMaxRestart + 1) * kMaxRestart];  // (restart+1) x restart, row-major with ld = restart
+    double e[kMaxRestart + 1];
+    double y[kMaxRestart];
+    double bnorm;
+    double rnorm;
+    double tmp[kMaxRestart + 2];
+    int iters;
+    int done;
+    int chol_info;   // 0 ok, k>0: pivot k of some instance was not positive
+    int pad;
+};
+
+}  // namespace pdeop

@@ -1,0 +1,529 @@
+// pdeop -- per-element bodies of the stencil kernels (host+device).
+//
+// Every function here handles ONE element (a grid point of one instance, a line position, ...).
+// The CUDA kernels in pdeop_cuda.cu map threads onto these bodies; the test-only CPU emulator in
+// tests/emu loops over them, so index algebra can be checked against the oracle without a GPU.
+//
+// Reference semantics restated here (paths relative to the reference repo):
+//   row structure / values     solver/lp_pde_central_diff.py:746-1033, 1300-1630
+//   K = A^T A, A^T b           solver/multigrid.py:210-240
+//   lexicographic Gauss-Seidel solver/multigrid.py:399-405
+//   linear grid transfer       solver/multigrid.py:243-268, 340-391 (F.interpolate, align_corners=True)
+//   gradients                  solver/qp_dual_sparse_multigrid_normal_kkt.py:112-162
+#pragma once
+#include "pdeop_common.h"
+
+#ifndef PDEOP_ATOMIC_ADD
+#if defined(__CUDA_ARCH__)
+#define PDEOP_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#else
+#define PDEOP_ATOMIC_ADD(p, v) (*(p) += (v))
+#endif
+#endif
+
+namespace pdeop {
+
+// 5-point stencil offsets of the central-difference row at line position i (lp_pde_central_diff.py:1000-1006):
+// one-sided at the two positions next to either end, centred otherwise.
+PDEOP_HD void stencil_offsets(int i, int n, int o[5]) {
+    if (i <= 1) {
+        for (int j = 0; j < 5; ++j) o[j] = j;
+    } else if (i >= n - 2) {
+        for (int j = 0; j < 5; ++j) o[j] = -j;
+    } else {
+        for (int j = 0; j < 5; ++j) o[j] = j - 2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Axis tables of K = A^T A.  One call per (instance, active axis a, padded position ip).
+//   cv [Ntot][2][6]  central rows: 5 stencil values on u + value on the own derivative channel
+//   fv [Ftot][4]     forward  rows at position i   : u[i], u_c[i], u_cc[i], u[i+1]
+//   bv [Ftot][4]     backward rows at position i+1 : u[i+1], u_c[i+1], u_cc[i+1], u[i]
+// Output Ta[e*P + ip], e in [0,30):
+//   T_UU+o+4 : K[u(i), u(i+o)]     T_UP+o+4 : K[u_c(i), u(i+o)]     T_UQ+o+4 : K[u_cc(i), u(i+o)]
+//   T_PP, T_QQ, T_PQ : K[u_c(i),u_c(i)], K[u_cc(i),u_cc(i)], K[u_c(i),u_cc(i)]      (axis part only)
+// ------------------------------------------------------------------------------------------------
+PDEOP_HD void build_table_elem(const LevelDev& L, int a, int ip, const double* cv, const double* fv,
+                               const double* bv, double* Ta) {
+    const int n = L.N[3 - L.D + a];
+    const int i = ip - kTabPad;
+    double t[kTabEntries];
+    for (int e = 0; e < kTabEntries; ++e) t[e] = 0.0;
+    if (i >= 0 && i < n) {
+        const double* cva = cv + (size_t)L.cvoff[a] * 12;
+        const double* fva = fv + (size_t)L.fvoff[a] * 4;
+        const double* bva = bv + (size_t)L.fvoff[a] * 4;
+        int lo = i - 4 < 0 ? 0 : i - 4;
+        int hi = i + 4 > n - 1 ? n - 1 : i + 4;
+        for (int ir = lo; ir <= hi; ++ir) {
+            int o[5];
+            stencil_offsets(ir, n, o);
+            int ji = -1;
+            for (int j = 0; j < 5; ++j)
+                if (ir + o[j] == i) ji = j;
+            if (ji < 0) continue;
+            for (int k = 0; k < 2; ++k) {
+                const double* row = cva + ((size_t)ir * 2 + k) * 6;
+                const double wi = row[ji];
+                for (int j2 = 0; j2 < 5; ++j2) t[T_UU + (ir + o[j2] - i) + 4] += wi * row[j2];
+            }
+        }
+        {
+            int o[5];
+            stencil_offsets(i, n, o);
+            const double* r1 = cva + ((size_t)i * 2 + 0) * 6;
+            const double* r2 = cva + ((size_t)i * 2 + 1) * 6;
+            for (int j = 0; j < 5; ++j) {
+                t[T_UP + o[j] + 4] += r1[5] * r1[j];
+                t[T_UQ + o[j] + 4] += r2[5] * r2[j];
+            }
+            t[T_PP] += r1[5] * r1[5];
+            t[T_QQ] += r2[5] * r2[5];
+        }
+        if (i <= n - 2) {  // forward row at i
+            const double* f = fva + (size_t)i * 4;
+            t[T_UU + 4] += f[0] * f[0];
+            t[T_UU + 5] += f[0] * f[3];
+            t[T_UP + 4] += f[1] * f[0];
+            t[T_UP + 5] += f[1] * f[3];
+            t[T_UQ + 4] += f[2] * f[0];
+            t[T_UQ + 5] += f[2] * f[3];
+            t[T_PP] += f[1] * f[1];
+            t[T_QQ] += f[2] * f[2];
+            t[T_PQ] += f[1] * f[2];
+        }
+        if (i >= 1) {  // forward row at i-1 touches u(i) as "next"
+            const double* f = fva + (size_t)(i - 1) * 4;
+            t[T_UU + 4] += f[3] * f[3];
+            t[T_UU + 3] += f[0] * f[3];
+        }
+        if (i >= 1) {  // backward row at i
+            const double* g = bva + (size_t)(i - 1) * 4;
+            t[T_UU + 4] += g[0] * g[0];
+            t[T_UU + 3] += g[0] * g[3];
+            t[T_UP + 4] += g[1] * g[0];
+            t[T_UP + 3] += g[1] * g[3];
+            t[T_UQ + 4] += g[2] * g[0];
+            t[T_UQ + 3] += g[2] * g[3];
+            t[T_PP] += g[1] * g[1];
+            t[T_QQ] += g[2] * g[2];
+            t[T_PQ] += g[1] * g[2];
+        }
+        if (i <= n - 2) {  // backward row at i+1 touches u(i) as "previous"
+            const double* g = bva + (size_t)i * 4;
+            t[T_UU + 4] += g[3] * g[3];
+            t[T_UU + 5] += g[0] * g[3];
+        }
+    }
+    for (int e = 0; e < kTabEntries; ++e) Ta[(size_t)e * L.P + ip] = t[e];
+}
+
+// wave index of the neighbour at offset o along internal axis AX
+template <int AX>
+PDEOP_HD int neighbor_pos(const LevelDev& L, int s, int i0, int i1, int o) {
+    if (AX == 2) return L.rowbase[(s + o + 4) * L.N[0] + i0] + i1;
+    if (AX == 1) return L.rowbase[(s + o + 4) * L.N[0] + i0] + i1 + o;
+    return L.rowbase[(s + o + 4) * L.N[0] + i0 + o] + i1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// acc[m] = sum over OFF-POINT couplings  K[(g,m),(g',m')] x[g',m'],  g' = g + o e_a, o in [-4,4]\{0}
+// T: instance tables [D][30][P];  x: instance vector [M][G]
+// ------------------------------------------------------------------------------------------------
+template <int D>
+PDEOP_HD void k_neighbors(const LevelDev& L, const double* __restrict__ T, const double* __restrict__ x, int i0,
+                          int i1, int i2, double acc[1 + 2 * D]) {
+    const int G = L.G, P = L.P;
+    const int s = i0 + i1 + i2;
+    const int idx[3] = {i0, i1, i2};
+#pragma unroll
+    for (int m = 0; m < 1 + 2 * D; ++m) acc[m] = 0.0;
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+        constexpr int kDummy = 0;
+        (void)kDummy;
+        const int ax = 3 - D + a;
+        const int n = L.N[ax];
+        const int i = idx[ax];
+        const double* __restrict__ Ta = T + (size_t)a * kTabEntries * P + (i + kTabPad);
+        double au = 0.0, ap = 0.0, aq = 0.0;
+#pragma unroll
+        for (int o = -4; o <= 4; ++o) {
+            if (o == 0) continue;
+            const int ii = i + o;
+            if (ii < 0 || ii >= n) continue;
+            int wn;
+            if (ax == 2) wn = neighbor_pos<2>(L, s, i0, i1, o);
+            else if (ax == 1) wn = neighbor_pos<1>(L, s, i0, i1, o);
+            else wn = neighbor_pos<0>(L, s, i0, i1, o);
+            const double un = x[wn];
+            const double pn = x[(size_t)(1 + a) * G + wn];
+            const double qn = x[(size_t)(1 + D + a) * G + wn];
+            au += Ta[(T_UU + o + 4) * P] * un + Ta[(T_UP - o + 4) * P + o] * pn + Ta[(T_UQ - o + 4) * P + o] * qn;
+            ap += Ta[(T_UP + o + 4) * P] * un;
+            aq += Ta[(T_UQ + o + 4) * P] * un;
+        }
+        acc[0] += au;
+        acc[1 + a] += ap;
+        acc[1 + D + a] += aq;
+    }
+}
+
+// per-point local quantities: equation-row coefficients c[m] (zero where the point has no equation
+// row), initial-row multiplicities, and the axis tables' same-point entries.
+template <int D>
+struct PointLocal {
+    double c[1 + 2 * D];
+    double ini[1 + 2 * D];
+    double uu;          // sum over axes of K[u,u] axis part
+    double up[D], uq[D], pp[D], qq[D], pq[D];
+};
+
+template <int D>
+PDEOP_HD void load_local(const LevelDev& L, const double* __restrict__ T, const double* __restrict__ coef, int w,
+                         int i0, int i1, int i2, int flags, PointLocal<D>& pl) {
+    const int G = L.G, P = L.P;
+    const int idx[3] = {i0, i1, i2};
+    const bool eq = flags & 1;
+#pragma unroll
+    for (int m = 0; m < 1 + 2 * D; ++m) {
+        pl.c[m] = eq ? coef[(size_t)m * G + w] : 0.0;
+        pl.ini[m] = (double)((flags >> (4 + 2 * m)) & 3);
+    }
+    pl.uu = 0.0;
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+        const int i = idx[3 - D + a];
+        const double* __restrict__ Ta = T + (size_t)a * kTabEntries * P + (i + kTabPad);
+        pl.uu += Ta[(T_UU + 4) * P];
+        pl.up[a] = Ta[(T_UP + 4) * P];
+        pl.uq[a] = Ta[(T_UQ + 4) * P];
+        pl.pp[a] = Ta[T_PP * P];
+        pl.qq[a] = Ta[T_QQ * P];
+        pl.pq[a] = Ta[T_PQ * P];
+    }
+}
+
+// y = K x at one point (mode 0) or y = b - K x (mode 1)
+template <int D>
+PDEOP_HD void apply_k_elem(const LevelDev& L, const double* __restrict__ T, const double* __restrict__ coef,
+                           const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ y,
+                           int w, int mode) {
+    constexpr int M = 1 + 2 * D;
+    const int G = L.G;
+    int i0, i1, i2;
+    unpack_coord(L.coord[w], i0, i1, i2);
+    const int flags = L.flags[w];
+    double acc[M];
+    k_neighbors<D>(L, T, x, i0, i1, i2, acc);
+    PointLocal<D> pl;
+    load_local<D>(L, T, coef, w, i0, i1, i2, flags, pl);
+    double xl[M];
+    double cs = 0.0;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        xl[m] = x[(size_t)m * G + w];
+        cs += pl.c[m] * xl[m];
+    }
+    double yl[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) yl[m] = acc[m] + pl.c[m] * cs + pl.ini[m] * xl[m];
+    yl[0] += pl.uu * xl[0];
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+        yl[0] += pl.up[a] * xl[1 + a] + pl.uq[a] * xl[1 + D + a];
+        yl[1 + a] += pl.up[a] * xl[0] + pl.pp[a] * xl[1 + a] + pl.pq[a] * xl[1 + D + a];
+        yl[1 + D + a] += pl.uq[a] * xl[0] + pl.pq[a] * xl[1 + a] + pl.qq[a] * xl[1 + D + a];
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const size_t k = (size_t)m * G + w;
+        y[k] = mode ? (b[k] - yl[m]) : yl[m];
+    }
+}
+
+// One lexicographic Gauss-Seidel update of the M unknowns of point w (channel order 0..M-1):
+//   x_j <- (b_j - sum_{k != j} K_jk x_k) / K_jj   with already-updated values for k < j.
+template <int D>
+PDEOP_HD void gs_elem(const LevelDev& L, const double* __restrict__ T, const double* __restrict__ coef,
+                      const double* __restrict__ b, double* x, int w) {
+    constexpr int M = 1 + 2 * D;
+    const int G = L.G;
+    int i0, i1, i2;
+    unpack_coord(L.coord[w], i0, i1, i2);
+    const int flags = L.flags[w];
+    double acc[M];
+    k_neighbors<D>(L, T, x, i0, i1, i2, acc);
+    PointLocal<D> pl;
+    load_local<D>(L, T, coef, w, i0, i1, i2, flags, pl);
+    double xl[M], r[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        xl[m] = x[(size_t)m * G + w];
+        r[m] = b[(size_t)m * G + w] - acc[m];
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < M; ++k)
+            if (k != m) t += pl.c[k] * xl[k];
+        double off = pl.c[m] * t;
+        double diag = pl.c[m] * pl.c[m] + pl.ini[m];
+        if (m == 0) {
+            diag += pl.uu;
+#pragma unroll
+            for (int a = 0; a < D; ++a) off += pl.up[a] * xl[1 + a] + pl.uq[a] * xl[1 + D + a];
+        } else if (m <= D) {
+            const int a = m - 1;
+            diag += pl.pp[a];
+            off += pl.up[a] * xl[0] + pl.pq[a] * xl[1 + D + a];
+        } else {
+            const int a = m - 1 - D;
+            diag += pl.qq[a];
+            off += pl.uq[a] * xl[0] + pl.pq[a] * xl[1 + a];
+        }
+        xl[m] = (r[m] - off) / diag;
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) x[(size_t)m * G + w] = xl[m];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Linear grid transfer (align_corners=True), C channels, wave layout on both sides.
+// out[m][wo] (=|+=) interp(in)[m] at the output point wo.
+// ------------------------------------------------------------------------------------------------
+PDEOP_HD void interp_axis(int i, int n_in, int n_out, int& lo, int& hi, double& l0, double& l1) {
+    const double scale = n_out > 1 ? (double)(n_in - 1) / (double)(n_out - 1) : 0.0;
+    const double src = scale * (double)i;
+    lo = (int)src;
+    if (lo > n_in - 1) lo = n_in - 1;
+    hi = lo + (lo < n_in - 1 ? 1 : 0);
+    l1 = src - (double)lo;
+    l0 = 1.0 - l1;
+}
+
+PDEOP_HD void interp_elem(const LevelDev& Li, const LevelDev& Lo, int C, const double* __restrict__ in,
+                          double* __restrict__ out, int wo, int add) {
+    int i0, i1, i2;
+    unpack_coord(Lo.coord[wo], i0, i1, i2);
+    int l[3], h[3];
+    double w0[3], w1[3];
+    interp_axis(i0, Li.N[0], Lo.N[0], l[0], h[0], w0[0], w1[0]);
+    interp_axis(i1, Li.N[1], Lo.N[1], l[1], h[1], w0[1], w1[1]);
+    interp_axis(i2, Li.N[2], Lo.N[2], l[2], h[2], w0[2], w1[2]);
+    const int p000 = wave_pos(Li, l[0], l[1], l[2]), p001 = wave_pos(Li, l[0], l[1], h[2]);
+    const int p010 = wave_pos(Li, l[0], h[1], l[2]), p011 = wave_pos(Li, l[0], h[1], h[2]);
+    const int p100 = wave_pos(Li, h[0], l[1], l[2]), p101 = wave_pos(Li, h[0], l[1], h[2]);
+    const int p110 = wave_pos(Li, h[0], h[1], l[2]), p111 = wave_pos(Li, h[0], h[1], h[2]);
+    for (int m = 0; m < C; ++m) {
+        const double* __restrict__ s = in + (size_t)m * Li.G;
+        const double v = w0[0] * (w0[1] * (w0[2] * s[p000] + w1[2] * s[p001]) + w1[1] * (w0[2] * s[p010] + w1[2] * s[p011])) +
+                         w1[0] * (w0[1] * (w0[2] * s[p100] + w1[2] * s[p101]) + w1[1] * (w0[2] * s[p110] + w1[2] * s[p111]));
+        const size_t k = (size_t)m * Lo.G + wo;
+        out[k] = add ? out[k] + v : v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout conversion between the operator surface (B,G,M) natural order and wave/planar order
+// ------------------------------------------------------------------------------------------------
+PDEOP_HD void pack_elem(const LevelDev& L, const double* __restrict__ api, double* __restrict__ wave, int w) {
+    int i0, i1, i2;
+    unpack_coord(L.coord[w], i0, i1, i2);
+    const size_t g = (size_t)nat_index(L, i0, i1, i2);
+    for (int m = 0; m < L.M; ++m) wave[(size_t)m * L.G + w] = api[g * L.M + m];
+}
+
+PDEOP_HD void unpack_elem(const LevelDev& L, const double* __restrict__ wave, double* __restrict__ api, int w) {
+    int i0, i1, i2;
+    unpack_coord(L.coord[w], i0, i1, i2);
+    const size_t g = (size_t)nat_index(L, i0, i1, i2);
+    for (int m = 0; m < L.M; ++m) api[g * L.M + m] = wave[(size_t)m * L.G + w];
+}
+
+// A^T b restricted to equation rows: atb[m][w] = c[m] * rhs[g]   (initial rows added by atb_init_elem)
+PDEOP_HD void atb_elem(const LevelDev& L, const double* __restrict__ coef, const double* __restrict__ rhs_nat,
+                       double* __restrict__ atb, int w) {
+    int i0, i1, i2;
+    unpack_coord(L.coord[w], i0, i1, i2);
+    const bool eq = L.flags[w] & 1;
+    const double r = eq ? rhs_nat[nat_index(L, i0, i1, i2)] : 0.0;
+    for (int m = 0; m < L.M; ++m) atb[(size_t)m * L.G + w] = eq ? coef[(size_t)m * L.G + w] * r : 0.0;
+}
+
+PDEOP_HD void atb_init_elem(const LevelDev& L, const double* __restrict__ iv_rhs, double* atb, int k) {
+    PDEOP_ATOMIC_ADD(&atb[(size_t)L.init_m[k] * L.G + L.init_w[k]], iv_rhs[k]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dense K for one point: writes the M rows (m*G+w) of the pre-zeroed n x n matrix (n = M*G).
+// ------------------------------------------------------------------------------------------------
+template <int D>
+PDEOP_HD void dense_elem(const LevelDev& L, const double* __restrict__ T, const double* __restrict__ coef,
+                         double* __restrict__ Kd, int w) {
+    constexpr int M = 1 + 2 * D;
+    const int G = L.G, P = L.P;
+    const size_t n = (size_t)M * G;
+    int i0, i1, i2;
+    unpack_coord(L.coord[w], i0, i1, i2);
+    const int flags = L.flags[w];
+    const int s = i0 + i1 + i2;
+    const int idx[3] = {i0, i1, i2};
+    PointLocal<D> pl;
+    load_local<D>(L, T, coef, w, i0, i1, i2, flags, pl);
+    // local block
+    for (int m = 0; m < M; ++m)
+        for (int k = 0; k < M; ++k) {
+            double v = pl.c[m] * pl.c[k];
+            if (m == k) v += pl.ini[m];
+            Kd[((size_t)m * G + w) * n + (size_t)k * G + w] = v;
+        }
+    Kd[(size_t)w * n + w] += pl.uu;
+    for (int a = 0; a < D; ++a) {
+        const size_t ru = w, rp = (size_t)(1 + a) * G + w, rq = (size_t)(1 + D + a) * G + w;
+        Kd[ru * n + rp] += pl.up[a];
+        Kd[rp * n + ru] += pl.up[a];
+        Kd[ru * n + rq] += pl.uq[a];
+        Kd[rq * n + ru] += pl.uq[a];
+        Kd[rp * n + rp] += pl.pp[a];
+        Kd[rq * n + rq] += pl.qq[a];
+        Kd[rp * n + rq] += pl.pq[a];
+        Kd[rq * n + rp] += pl.pq[a];
+    }
+    // neighbours
+    for (int a = 0; a < D; ++a) {
+        const int ax = 3 - D + a;
+        const int nn = L.N[ax];
+        const int i = idx[ax];
+        const double* Ta = T + (size_t)a * kTabEntries * P + (i + kTabPad);
+        const size_t ru = w, rp = (size_t)(1 + a) * G + w, rq = (size_t)(1 + D + a) * G + w;
+        for (int o = -4; o <= 4; ++o) {
+            if (o == 0) continue;
+            const int ii = i + o;
+            if (ii < 0 || ii >= nn) continue;
+            int wn;
+            if (ax == 2) wn = neighbor_pos<2>(L, s, i0, i1, o);
+            else if (ax == 1) wn = neighbor_pos<1>(L, s, i0, i1, o);
+            else wn = neighbor_pos<0>(L, s, i0, i1, o);
+            Kd[ru * n + wn] = Ta[(T_UU + o + 4) * P];
+            Kd[ru * n + (size_t)(1 + a) * G + wn] = Ta[(T_UP - o + 4) * P + o];
+            Kd[ru * n + (size_t)(1 + D + a) * G + wn] = Ta[(T_UQ - o + 4) * P + o];
+            Kd[rp * n + wn] = Ta[(T_UP + o + 4) * P];
+            Kd[rq * n + wn] = Ta[(T_UQ + o + 4) * P];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gradients at one point (qp_dual_sparse_multigrid_normal_kkt.py:112-162):
+//   lam = b - A x, dnu = -A dz;  dA_r = lam_r dz^T + dnu_r x^T on the pattern of row r;  db = A dz.
+// Outputs: d_coeffs (G,M) natural, d_rhs (G) natural, and atomically accumulated gradients of the
+// per-line row values d_cv [Ntot][2][6], d_fv [Ftot][4], d_bv [Ftot][4] (the reference's per-nnz dD
+// summed over the grid directions a line value is expanded along).
+// ------------------------------------------------------------------------------------------------
+template <int D>
+PDEOP_HD void grad_elem(const LevelDev& L, const double* __restrict__ coef, const double* __restrict__ rhs_nat,
+                        const double* __restrict__ cv, const double* __restrict__ fv, const double* __restrict__ bv,
+                        const double* __restrict__ x, const double* __restrict__ dz, double* __restrict__ d_coeffs,
+                        double* __restrict__ d_rhs, double* d_cv, double* d_fv, double* d_bv, int w) {
+    constexpr int M = 1 + 2 * D;
+    const int G = L.G;
+    int i0, i1, i2;
+    unpack_coord(L.coord[w], i0, i1, i2);
+    const int flags = L.flags[w];
+    const int s = i0 + i1 + i2;
+    const int idx[3] = {i0, i1, i2};
+    const size_t g = (size_t)nat_index(L, i0, i1, i2);
+    double xl[M], zl[M];
+    for (int m = 0; m < M; ++m) {
+        xl[m] = x[(size_t)m * G + w];
+        zl[m] = dz[(size_t)m * G + w];
+    }
+    if (flags & 1) {
+        double cx = 0.0, cz = 0.0;
+        for (int m = 0; m < M; ++m) {
+            const double c = coef[(size_t)m * G + w];
+            cx += c * xl[m];
+            cz += c * zl[m];
+        }
+        const double lam = rhs_nat[g] - cx;
+        for (int m = 0; m < M; ++m) d_coeffs[g * M + m] = lam * zl[m] - cz * xl[m];
+        d_rhs[g] = cz;
+    } else {
+        for (int m = 0; m < M; ++m) d_coeffs[g * M + m] = 0.0;
+        d_rhs[g] = 0.0;
+    }
+    for (int a = 0; a < D; ++a) {
+        const int ax = 3 - D + a;
+        const int n = L.N[ax];
+        const int i = idx[ax];
+        // central rows (i, k)
+        int o[5];
+        stencil_offsets(i, n, o);
+        double ux[5], uz[5];
+        for (int j = 0; j < 5; ++j) {
+            int wn;
+            if (o[j] == 0) wn = w;
+            else if (ax == 2) wn = neighbor_pos<2>(L, s, i0, i1, o[j]);
+            else if (ax == 1) wn = neighbor_pos<1>(L, s, i0, i1, o[j]);
+            else wn = neighbor_pos<0>(L, s, i0, i1, o[j]);
+            ux[j] = x[wn];
+            uz[j] = dz[wn];
+        }
+        for (int k = 0; k < 2; ++k) {
+            const size_t ro = ((size_t)(L.cvoff[a] + i) * 2 + k) * 6;
+            const double* row = cv + ro;
+            const int ch = k == 0 ? 1 + a : 1 + D + a;
+            double rx = row[5] * xl[ch], rz = row[5] * zl[ch];
+            for (int j = 0; j < 5; ++j) {
+                rx += row[j] * ux[j];
+                rz += row[j] * uz[j];
+            }
+            for (int j = 0; j < 5; ++j) PDEOP_ATOMIC_ADD(&d_cv[ro + j], -rx * uz[j] - rz * ux[j]);
+            PDEOP_ATOMIC_ADD(&d_cv[ro + 5], -rx * zl[ch] - rz * xl[ch]);
+        }
+        // forward row at this point: u, u_c, u_cc, u(next)
+        if (i <= n - 2) {
+            int wn;
+            if (ax == 2) wn = neighbor_pos<2>(L, s, i0, i1, 1);
+            else if (ax == 1) wn = neighbor_pos<1>(L, s, i0, i1, 1);
+            else wn = neighbor_pos<0>(L, s, i0, i1, 1);
+            const size_t ro = (size_t)(L.fvoff[a] + i) * 4;
+            const double* f = fv + ro;
+            const double vx[4] = {xl[0], xl[1 + a], xl[1 + D + a], x[wn]};
+            const double vz[4] = {zl[0], zl[1 + a], zl[1 + D + a], dz[wn]};
+            double rx = 0.0, rz = 0.0;
+            for (int j = 0; j < 4; ++j) {
+                rx += f[j] * vx[j];
+                rz += f[j] * vz[j];
+            }
+            for (int j = 0; j < 4; ++j) PDEOP_ATOMIC_ADD(&d_fv[ro + j], -rx * vz[j] - rz * vx[j]);
+        }
+        // backward row at this point: u, u_c, u_cc, u(prev); table entry i-1
+        if (i >= 1) {
+            int wn;
+            if (ax == 2) wn = neighbor_pos<2>(L, s, i0, i1, -1);
+            else if (ax == 1) wn = neighbor_pos<1>(L, s, i0, i1, -1);
+            else wn = neighbor_pos<0>(L, s, i0, i1, -1);
+            const size_t ro = (size_t)(L.fvoff[a] + i - 1) * 4;
+            const double* f = bv + ro;
+            const double vx[4] = {xl[0], xl[1 + a], xl[1 + D + a], x[wn]};
+            const double vz[4] = {zl[0], zl[1 + a], zl[1 + D + a], dz[wn]};
+            double rx = 0.0, rz = 0.0;
+            for (int j = 0; j < 4; ++j) {
+                rx += f[j] * vx[j];
+                rz += f[j] * vz[j];
+            }
+            for (int j = 0; j < 4; ++j) PDEOP_ATOMIC_ADD(&d_bv[ro + j], -rx * vz[j] - rz * vx[j]);
+        }
+    }
+}
+
+// d(iv_rhs)[k] = (A dz)_init,k = dz at the row's variable
+PDEOP_HD void grad_init_elem(const LevelDev& L, const double* __restrict__ dz, double* __restrict__ d_iv, int k) {
+    d_iv[k] = dz[(size_t)L.init_m[k] * L.G + L.init_w[k]];
+}
+
+}  // namespace pdeop

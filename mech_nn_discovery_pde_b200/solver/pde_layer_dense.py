@@ -1,0 +1,67 @@
+"""``PDEDenseLayer``: the reference's dense-KKT PDE layer (solver/pde_layer_dense.py:38-125) on the
+B200-native dense path.  Same constructor, same ``forward(coeffs, rhs, iv_rhs, steps_list) -> (u0, u, eps)``.
+"""
+import torch
+import torch.nn as nn
+
+from ..config import PDEConfig
+from ..ops import DenseSolveFn, PdePlan, new_holder
+from .line_values import line_values
+from .lp_pde_central_diff import PDESYSLP
+
+
+class PDEDenseLayer(nn.Module):
+    """Dense PDE layer (pde_layer_dense.py:38-125)."""
+
+    def __init__(self, bs, order, n_ind_dim, n_iv, init_index_mi_list, coord_dims, n_iv_steps, solver_dbl=True,
+                 evolution=False, gamma=0.5, alpha=0.1, double_ret=False, device=None, _library=None):
+        super().__init__()
+        self.step_size = 0.01
+        self.coord_dims = tuple(int(v) for v in coord_dims)
+        self.n_coord = len(self.coord_dims)
+        self.order = order
+        self.n_ind_dim = n_ind_dim
+        self.n_dim = 1
+        self.n_equations = 1
+        self.n_iv = n_iv
+        self.n_iv_steps = 1
+        self.bs = bs
+        self.device = device
+        self.solver_dbl = solver_dbl
+        self.evolution = evolution
+        self.double_ret = double_ret
+        self.plan = PdePlan(self.coord_dims, order, bs * n_ind_dim, 1, True, init_index_mi_list, library=_library)
+        # the reference builds the dense layer's constraints with evolution=False whatever is passed
+        # (pde_layer_dense.py:72-75)
+        self.pde = PDESYSLP(bs * n_ind_dim, self.coord_dims, order, n_iv, init_index_mi_list, self.plan.n_init,
+                            evolution=False, dtype=torch.float64)
+        self.n_orders = len(self.pde.var_set.mi_list)
+        self.grid_size = self.pde.var_set.grid_size
+        self.step_grid_shape = self.pde.step_grid_shape
+        self.config = PDEConfig
+        self.last_holder = None
+
+    def forward(self, coeffs, rhs, iv_rhs, steps_list):
+        B = self.bs * self.n_ind_dim
+        coeffs = coeffs.reshape(B, self.grid_size, self.n_orders)
+        rhs = rhs.reshape(B, self.grid_size)
+        if iv_rhs is not None:
+            iv_rhs = iv_rhs.reshape(B, -1)
+        else:
+            iv_rhs = rhs.new_zeros(B, 0)
+        for i in range(self.n_coord):   # pde_layer_dense.py:95-97
+            steps_list[i] = steps_list[i].reshape(B, self.coord_dims[i] - 1)
+        coeffs = coeffs.double()
+        rhs = rhs.double()
+        iv_rhs = iv_rhs.double()
+        steps = [s.double() for s in steps_list]
+
+        cv, fv, bv = line_values(steps)
+        holder = new_holder(self.plan, [], self.config)
+        x = DenseSolveFn.apply(coeffs, rhs, iv_rhs, cv, fv, bv, holder)
+        self.last_holder = holder
+        eps = None
+        u = self.pde.get_solution_reshaped(x)
+        u = u.reshape(self.bs, self.n_ind_dim, *u.shape[1:])
+        u0 = u[:, :, :, 0]
+        return u0, u, eps

@@ -1,0 +1,261 @@
+// TEST INFRASTRUCTURE ONLY -- CPU emulator of the pdeop backend.
+//
+// Implements pdeop_backend.h with plain sequential loops over the SAME per-element bodies
+// (csrc/pdeop_elem.h) the CUDA kernels call, so that the index algebra, the axis tables, the
+// wavefront Gauss-Seidel ordering and the host-side orchestration (V-cycle, FGMRES, gradients) can be
+// checked against the oracle in a container without a GPU.  It is built into
+// tests/emu/libpdeop_emu.so by tests/emu/build.py and loaded only by tests.  The product package
+// never loads it: mech_nn_discovery_pde_b200 raises if the CUDA library or a GPU is missing.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../mech_nn_discovery_pde_b200/csrc/pdeop_backend.h"
+#include "../../mech_nn_discovery_pde_b200/csrc/pdeop_elem.h"
+
+namespace pdeop {
+
+static int g_gs_reverse = 0;  // process pipelined sweeps in reverse order inside a step (order-independence check)
+extern "C" void pdeop_emu_set_gs_reverse(int v) { g_gs_reverse = v; }
+
+const char* be_name() { return "host-emulator"; }
+void* be_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
+void be_free(void* p) { free(p); }
+void be_upload(void* dst, const void* src, size_t bytes) { if (bytes) memcpy(dst, src, bytes); }
+void be_zero(stream_t, void* p, size_t bytes) { memset(p, 0, bytes); }
+int be_last_error(char*, int) { return 0; }
+
+static inline size_t vstride(const LevelDev& L) { return (size_t)L.M * L.G; }
+static inline size_t tstride(const LevelDev& L) { return (size_t)L.D * kTabEntries * L.P; }
+
+void be_build_tables(stream_t, const LevelDev& L, int B, const double* cv, const double* fv, const double* bv,
+                     double* T) {
+    for (int b = 0; b < B; ++b)
+        for (int a = 0; a < L.D; ++a)
+            for (int ip = 0; ip < L.P; ++ip)
+                build_table_elem(L, a, ip, cv + (size_t)b * L.Ntot * 12, fv + (size_t)b * L.Ftot * 4,
+                                 bv + (size_t)b * L.Ftot * 4, T + b * tstride(L) + (size_t)a * kTabEntries * L.P);
+}
+
+void be_pack(stream_t, const LevelDev& L, int B, const double* api, double* wave) {
+    for (int b = 0; b < B; ++b)
+        for (int w = 0; w < L.G; ++w) pack_elem(L, api + b * vstride(L), wave + b * vstride(L), w);
+}
+
+void be_unpack(stream_t, const LevelDev& L, int B, const double* wave, double* api) {
+    for (int b = 0; b < B; ++b)
+        for (int w = 0; w < L.G; ++w) unpack_elem(L, wave + b * vstride(L), api + b * vstride(L), w);
+}
+
+void be_interp(stream_t, const LevelDev& Li, const LevelDev& Lo, int B, int C, const double* in, double* out, int add,
+               const int* done) {
+    if (done && *done) return;
+    for (int b = 0; b < B; ++b)
+        for (int w = 0; w < Lo.G; ++w)
+            interp_elem(Li, Lo, C, in + (size_t)b * C * Li.G, out + (size_t)b * C * Lo.G, w, add);
+}
+
+void be_atb(stream_t, const LevelDev& L, int B, const double* coef, const double* rhs_nat, const double* iv_rhs,
+            double* atb) {
+    for (int b = 0; b < B; ++b) {
+        for (int w = 0; w < L.G; ++w) atb_elem(L, coef + b * vstride(L), rhs_nat + (size_t)b * L.G, atb + b * vstride(L), w);
+        for (int k = 0; k < L.n_init; ++k) atb_init_elem(L, iv_rhs + (size_t)b * L.n_init, atb + b * vstride(L), k);
+    }
+}
+
+template <int D>
+static void apply_k_t(const LevelDev& L, int B, const double* T, const double* coef, const double* x, const double* b,
+                      double* y, int mode) {
+    for (int ib = 0; ib < B; ++ib)
+        for (int w = 0; w < L.G; ++w)
+            apply_k_elem<D>(L, T + ib * tstride(L), coef + ib * vstride(L), x + ib * vstride(L),
+                            b ? b + ib * vstride(L) : nullptr, y + ib * vstride(L), w, mode);
+}
+
+void be_apply_k(stream_t, const LevelDev& L, int B, const double* T, const double* coef, const double* x,
+                const double* b, double* y, int mode, const int* done) {
+    if (done && *done) return;
+    if (L.D == 1) apply_k_t<1>(L, B, T, coef, x, b, y, mode);
+    else if (L.D == 2) apply_k_t<2>(L, B, T, coef, x, b, y, mode);
+    else apply_k_t<3>(L, B, T, coef, x, b, y, mode);
+}
+
+template <int D>
+static void gs_t(const LevelDev& L, int B, const double* T, const double* coef, const double* b, double* x,
+                 int nsweeps) {
+    std::vector<int> hs(L.S + 1);
+    memcpy(hs.data(), L.hstart, sizeof(int) * (L.S + 1));
+    const int steps = L.S + kGsLag * (nsweeps - 1);
+    for (int ib = 0; ib < B; ++ib)
+        for (int t = 0; t < steps; ++t)
+            for (int kk = 0; kk < nsweeps; ++kk) {
+                const int k = g_gs_reverse ? nsweeps - 1 - kk : kk;
+                const int s = t - kGsLag * k;
+                if (s < 0 || s >= L.S) continue;
+                for (int w = hs[s]; w < hs[s + 1]; ++w)
+                    gs_elem<D>(L, T + ib * tstride(L), coef + ib * vstride(L), b + ib * vstride(L),
+                               x + ib * vstride(L), w);
+            }
+}
+
+void be_gs(stream_t, const LevelDev& L, int B, const double* T, const double* coef, const double* b, double* x,
+           int nsweeps, const int* done, int) {
+    if (done && *done) return;
+    if (nsweeps <= 0) return;
+    if (L.D == 1) gs_t<1>(L, B, T, coef, b, x, nsweeps);
+    else if (L.D == 2) gs_t<2>(L, B, T, coef, b, x, nsweeps);
+    else gs_t<3>(L, B, T, coef, b, x, nsweeps);
+}
+
+void be_dense(stream_t, const LevelDev& L, int B, const double* T, const double* coef, double* Kd) {
+    const size_t n = vstride(L);
+    for (int ib = 0; ib < B; ++ib)
+        for (int w = 0; w < L.G; ++w) {
+            if (L.D == 1) dense_elem<1>(L, T + ib * tstride(L), coef + ib * n, Kd + ib * n * n, w);
+            else if (L.D == 2) dense_elem<2>(L, T + ib * tstride(L), coef + ib * n, Kd + ib * n * n, w);
+            else dense_elem<3>(L, T + ib * tstride(L), coef + ib * n, Kd + ib * n * n, w);
+        }
+}
+
+void be_cholesky(stream_t, int B, int n, double* Kd, FgmresState* state) {
+    for (int ib = 0; ib < B; ++ib) {
+        double* A = Kd + (size_t)ib * n * n;
+        for (int j = 0; j < n; ++j) {
+            double d = A[(size_t)j * n + j];
+            for (int k = 0; k < j; ++k) d -= A[(size_t)j * n + k] * A[(size_t)j * n + k];
+            if (!(d > 0.0)) {
+                if (state->chol_info == 0) state->chol_info = j + 1;
+                d = 1.0;
+            }
+            d = sqrt(d);
+            A[(size_t)j * n + j] = d;
+            for (int i = j + 1; i < n; ++i) {
+                double v = A[(size_t)i * n + j];
+                for (int k = 0; k < j; ++k) v -= A[(size_t)i * n + k] * A[(size_t)j * n + k];
+                A[(size_t)i * n + j] = v / d;
+            }
+        }
+    }
+}
+
+void be_chol_solve(stream_t, int B, int n, const double* Lf, const double* rhs, double* out, double*,
+                   const int* done) {
+    if (done && *done) return;
+    for (int ib = 0; ib < B; ++ib) {
+        const double* A = Lf + (size_t)ib * n * n;
+        const double* r = rhs + (size_t)ib * n;
+        double* y = out + (size_t)ib * n;
+        for (int i = 0; i < n; ++i) {
+            double v = r[i];
+            for (int k = 0; k < i; ++k) v -= A[(size_t)i * n + k] * y[k];
+            y[i] = v / A[(size_t)i * n + i];
+        }
+        for (int i = n - 1; i >= 0; --i) {
+            double v = y[i];
+            for (int k = i + 1; k < n; ++k) v -= A[(size_t)k * n + i] * y[k];
+            y[i] = v / A[(size_t)i * n + i];
+        }
+    }
+}
+
+void be_grads(stream_t, const LevelDev& L, int B, const double* coef, const double* rhs_nat, const double* cv,
+              const double* fv, const double* bv, const double* x, const double* dz, double* d_coeffs, double* d_rhs,
+              double* d_iv, double* d_cv, double* d_fv, double* d_bv) {
+    const size_t n = vstride(L);
+    for (int ib = 0; ib < B; ++ib) {
+        const size_t oc = (size_t)ib * L.Ntot * 12, of = (size_t)ib * L.Ftot * 4;
+        for (int w = 0; w < L.G; ++w) {
+#define GRAD_CALL(DD)                                                                                              \
+    grad_elem<DD>(L, coef + ib * n, rhs_nat + (size_t)ib * L.G, cv + oc, fv + of, bv + of, x + ib * n, dz + ib * n, \
+                  d_coeffs + ib * n, d_rhs + (size_t)ib * L.G, d_cv + oc, d_fv + of, d_bv + of, w)
+            if (L.D == 1) GRAD_CALL(1);
+            else if (L.D == 2) GRAD_CALL(2);
+            else GRAD_CALL(3);
+#undef GRAD_CALL
+        }
+        for (int k = 0; k < L.n_init; ++k) grad_init_elem(L, dz + ib * n, d_iv + (size_t)ib * L.n_init, k);
+    }
+}
+
+// ---- FGMRES vector steps --------------------------------------------------------------------------
+static double nrm2(size_t n, const double* v) {
+    double s = 0.0;
+    for (size_t i = 0; i < n; ++i) s += v[i] * v[i];
+    return sqrt(s);
+}
+
+void be_state_reset(stream_t, FgmresState* s) { memset(s, 0, sizeof(*s)); }
+
+void be_fg_begin(stream_t, size_t n, const double* b, double* x, FgmresState* s) {
+    memset(x, 0, n * sizeof(double));
+    s->bnorm = nrm2(n, b);
+    s->iters = 0;
+    s->rnorm = 0.0;
+    s->done = (s->bnorm == 0.0) ? 1 : 0;  // fgmres.py:76-78
+}
+
+void be_fg_resnorm(stream_t, size_t n, const double* r, FgmresState* s, int maxiter, double atol) {
+    if (s->done) return;
+    s->rnorm = nrm2(n, r);
+    if (s->rnorm <= atol || s->iters >= maxiter) s->done = 1;  // fgmres.py:134
+    else s->e[0] = s->rnorm;
+}
+
+void be_fg_first(stream_t, size_t n, const double* r, double* V0, FgmresState* s) {
+    if (s->done) return;
+    for (size_t i = 0; i < n; ++i) V0[i] = r[i] / s->rnorm;
+}
+
+void be_fg_cgs(stream_t, size_t n, int j, int restart, double* V, double* w, FgmresState* s) {
+    if (s->done) return;
+    double h[kMaxRestart];
+    for (int k = 0; k <= j; ++k) {
+        double a = 0.0;
+        const double* vk = V + (size_t)k * n;
+        for (size_t i = 0; i < n; ++i) a += vk[i] * w[i];
+        h[k] = a;
+        s->H[k * restart + j] = a;
+    }
+    for (int k = 0; k <= j; ++k) {
+        const double* vk = V + (size_t)k * n;
+        for (size_t i = 0; i < n; ++i) w[i] -= h[k] * vk[i];
+    }
+    const double nn = nrm2(n, w);
+    s->H[(j + 1) * restart + j] = nn;
+    if (j + 1 < restart) {
+        double* vn = V + (size_t)(j + 1) * n;
+        for (size_t i = 0; i < n; ++i) vn[i] = w[i] / nn;
+    }
+}
+
+}  // namespace pdeop
+
+#include "../../mech_nn_discovery_pde_b200/csrc/pdeop_lstsq.h"
+
+namespace pdeop {
+
+void be_fg_update(stream_t, size_t n, int restart, const double* Z, double* x, FgmresState* s) {
+    if (s->done) return;
+    hessenberg_lstsq(s->H, s->e, restart, s->y);
+    for (int k = 0; k < restart; ++k) {
+        const double* zk = Z + (size_t)k * n;
+        const double yk = s->y[k];
+        for (size_t i = 0; i < n; ++i) x[i] += yk * zk[i];
+    }
+    s->iters += restart;
+}
+
+void be_fg_info(stream_t, const FgmresState* s, double* info4) {
+    info4[0] = s->iters;
+    info4[1] = s->rnorm;
+    info4[2] = s->bnorm;
+    info4[3] = s->chol_info;
+}
+
+void be_fg_hess(stream_t, const FgmresState* s, int restart, double* hess_out) {
+    memcpy(hess_out, s->H, sizeof(double) * (restart + 1) * restart);
+}
+
+}  // namespace pdeop
