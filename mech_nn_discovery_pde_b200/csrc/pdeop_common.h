@@ -77,4 +77,15 @@ struct FgmresState {
     int pad;
 };
 
+// Scratch area for two-phase reductions, placed right after the FgmresState in the scratch buffer:
+// two ping-pong areas of kReduceBlocks x (kMaxRestart+1) block partials.
+constexpr int kReduceBlocks = 592;   // 4 x 148 SMs
+constexpr size_t kStateBytes = (sizeof(FgmresState) + 255) / 256 * 256;
+constexpr size_t kPartialDoubles = (size_t)kReduceBlocks * (kMaxRestart + 1);
+constexpr size_t kStateAreaDoubles = kStateBytes / 8 + 2 * kPartialDoubles;
+
+PDEOP_HD double* state_partials(const FgmresState* s, int which) {
+    return (double*)((char*)s + kStateBytes) + (size_t)which * kPartialDoubles;
+}
+
 }  // namespace pdeop

@@ -1,0 +1,887 @@
+// pdeop -- CUDA backend for sm_100a (B200).  Implements pdeop_backend.h.
+//
+// Kernel families (all fp64, HBM-bound streams unless noted; see DESIGN.md for the rooflines):
+//   * stencil kernels over grid points in wave order: K apply / residual, wavefront Gauss-Seidel,
+//     linear grid transfer, A^T b, dense coarse K, gradients               (bodies in pdeop_elem.h)
+//   * Krylov vector kernels with fused multi-dot / multi-axpy / norm steps: warp-shuffle + block
+//     reductions, block partials re-summed in a fixed order by the consumer kernel (deterministic,
+//     no host synchronisation; the convergence flag lives in device memory)
+//   * batched dense Cholesky (blocked right-looking, two-level) and blocked triangular solves for the
+//     coarsest multigrid level and the dense layer
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "pdeop_backend.h"
+#include "pdeop_elem.h"
+#include "pdeop_lstsq.h"
+
+namespace cg = cooperative_groups;
+
+namespace pdeop {
+
+static thread_local cudaError_t g_cuda_err = cudaSuccess;
+static inline void note(cudaError_t e) {
+    if (e != cudaSuccess && g_cuda_err == cudaSuccess) g_cuda_err = e;
+}
+#define PDEOP_LAUNCH_CHECK() note(cudaGetLastError())
+
+const char* be_name() { return "cuda-sm100a"; }
+
+void* be_alloc(size_t bytes) {
+    void* p = nullptr;
+    note(cudaMalloc(&p, bytes ? bytes : 1));
+    return p;
+}
+void be_free(void* p) {
+    if (p) cudaFree(p);
+}
+void be_upload(void* dst, const void* src, size_t bytes) {
+    if (bytes) note(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+}
+void be_zero(stream_t st, void* p, size_t bytes) {
+    if (bytes) note(cudaMemsetAsync(p, 0, bytes, (cudaStream_t)st));
+}
+int be_last_error(char* buf, int len) {
+    cudaError_t e = g_cuda_err;
+    if (e == cudaSuccess) e = cudaPeekAtLastError();
+    if (e == cudaSuccess) return 0;
+    snprintf(buf, len, "%s", cudaGetErrorString(e));
+    g_cuda_err = cudaSuccess;
+    cudaGetLastError();
+    return 1;
+}
+
+constexpr int kThreads = 256;
+static inline size_t vstride(const LevelDev& L) { return (size_t)L.M * L.G; }
+static inline size_t tstride(const LevelDev& L) { return (size_t)L.D * kTabEntries * L.P; }
+static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// =================================================================================================
+// element-wise stencil kernels: one thread per grid point (wave order => coalesced own-point access)
+// =================================================================================================
+__global__ void __launch_bounds__(kThreads) k_build_tables(LevelDev L, const double* __restrict__ cv,
+                                                           const double* __restrict__ fv,
+                                                           const double* __restrict__ bv, double* __restrict__ T) {
+    const int ip = blockIdx.x * blockDim.x + threadIdx.x;
+    const int a = blockIdx.y, b = blockIdx.z;
+    if (ip >= L.P) return;
+    build_table_elem(L, a, ip, cv + (size_t)b * L.Ntot * 12, fv + (size_t)b * L.Ftot * 4, bv + (size_t)b * L.Ftot * 4,
+                     T + ((size_t)b * L.D + a) * kTabEntries * L.P);
+}
+
+void be_build_tables(stream_t st, const LevelDev& L, int B, const double* cv, const double* fv, const double* bv,
+                     double* T) {
+    dim3 grid(cdiv(L.P, kThreads), L.D, B);
+    k_build_tables<<<grid, kThreads, 0, (cudaStream_t)st>>>(L, cv, fv, bv, T);
+    PDEOP_LAUNCH_CHECK();
+}
+
+__global__ void __launch_bounds__(kThreads) k_pack(LevelDev L, const double* __restrict__ api,
+                                                   double* __restrict__ wave) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= L.G) return;
+    const size_t o = (size_t)blockIdx.y * L.M * L.G;
+    pack_elem(L, api + o, wave + o, w);
+}
+__global__ void __launch_bounds__(kThreads) k_unpack(LevelDev L, const double* __restrict__ wave,
+                                                     double* __restrict__ api) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= L.G) return;
+    const size_t o = (size_t)blockIdx.y * L.M * L.G;
+    unpack_elem(L, wave + o, api + o, w);
+}
+void be_pack(stream_t st, const LevelDev& L, int B, const double* api, double* wave) {
+    k_pack<<<dim3(cdiv(L.G, kThreads), B), kThreads, 0, (cudaStream_t)st>>>(L, api, wave);
+    PDEOP_LAUNCH_CHECK();
+}
+void be_unpack(stream_t st, const LevelDev& L, int B, const double* wave, double* api) {
+    k_unpack<<<dim3(cdiv(L.G, kThreads), B), kThreads, 0, (cudaStream_t)st>>>(L, wave, api);
+    PDEOP_LAUNCH_CHECK();
+}
+
+__global__ void __launch_bounds__(kThreads) k_interp(LevelDev Li, LevelDev Lo, int C, const double* __restrict__ in,
+                                                     double* __restrict__ out, int add, const int* done) {
+    if (done && *done) return;
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= Lo.G) return;
+    interp_elem(Li, Lo, C, in + (size_t)blockIdx.y * C * Li.G, out + (size_t)blockIdx.y * C * Lo.G, w, add);
+}
+void be_interp(stream_t st, const LevelDev& Li, const LevelDev& Lo, int B, int C, const double* in, double* out,
+               int add, const int* done) {
+    k_interp<<<dim3(cdiv(Lo.G, kThreads), B), kThreads, 0, (cudaStream_t)st>>>(Li, Lo, C, in, out, add, done);
+    PDEOP_LAUNCH_CHECK();
+}
+
+__global__ void __launch_bounds__(kThreads) k_atb(LevelDev L, const double* __restrict__ coef,
+                                                  const double* __restrict__ rhs_nat, double* __restrict__ atb) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= L.G) return;
+    const size_t o = (size_t)blockIdx.y * L.M * L.G;
+    atb_elem(L, coef + o, rhs_nat + (size_t)blockIdx.y * L.G, atb + o, w);
+}
+__global__ void __launch_bounds__(kThreads) k_atb_init(LevelDev L, const double* __restrict__ iv_rhs, double* atb) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= L.n_init) return;
+    atb_init_elem(L, iv_rhs + (size_t)blockIdx.y * L.n_init, atb + (size_t)blockIdx.y * L.M * L.G, k);
+}
+void be_atb(stream_t st, const LevelDev& L, int B, const double* coef, const double* rhs_nat, const double* iv_rhs,
+            double* atb) {
+    k_atb<<<dim3(cdiv(L.G, kThreads), B), kThreads, 0, (cudaStream_t)st>>>(L, coef, rhs_nat, atb);
+    PDEOP_LAUNCH_CHECK();
+    if (L.n_init > 0) {
+        k_atb_init<<<dim3(cdiv(L.n_init, kThreads), B), kThreads, 0, (cudaStream_t)st>>>(L, iv_rhs, atb);
+        PDEOP_LAUNCH_CHECK();
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_apply(LevelDev L, const double* __restrict__ T,
+                                                    const double* __restrict__ coef, const double* __restrict__ x,
+                                                    const double* __restrict__ b, double* __restrict__ y, int mode,
+                                                    const int* done) {
+    if (done && *done) return;
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= L.G) return;
+    const size_t o = (size_t)blockIdx.y * L.M * L.G;
+    apply_k_elem<D>(L, T + (size_t)blockIdx.y * L.D * kTabEntries * L.P, coef + o, x + o, b ? b + o : nullptr, y + o, w,
+                    mode);
+}
+void be_apply_k(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, const double* x,
+                const double* b, double* y, int mode, const int* done) {
+    dim3 grid(cdiv(L.G, kThreads), B);
+    cudaStream_t s = (cudaStream_t)st;
+    if (L.D == 1) k_apply<1><<<grid, kThreads, 0, s>>>(L, T, coef, x, b, y, mode, done);
+    else if (L.D == 2) k_apply<2><<<grid, kThreads, 0, s>>>(L, T, coef, x, b, y, mode, done);
+    else k_apply<3><<<grid, kThreads, 0, s>>>(L, T, coef, x, b, y, mode, done);
+    PDEOP_LAUNCH_CHECK();
+}
+
+// =================================================================================================
+// Wavefront Gauss-Seidel.  Lexicographic GS on K couples a point only with points at distance <= 4
+// along the grid axes, so all points of a hyperplane s = i0+i1+i2 are independent, and sweep k+1 may
+// work on hyperplane s-5 while sweep k works on s (kGsLag).  One thread-block cluster owns one
+// instance: per step it updates the points of up to `nsweeps` hyperplanes (one per in-flight sweep),
+// then the cluster barrier (release/acquire) orders the in-place iterate for the next step.
+// The iterate is read at the L2 coherence point (LdL2) because other CTAs of the cluster write it.
+// =================================================================================================
+constexpr int kGsThreads = 512;
+constexpr int kGsMaxSweeps = 16;
+
+template <int D>
+__global__ void __launch_bounds__(kGsThreads, 1) k_gs_cluster(LevelDev L, const double* __restrict__ T,
+                                                              const double* __restrict__ coef,
+                                                              const double* __restrict__ b, double* x, int nsweeps,
+                                                              const int* done) {
+    if (done && *done) return;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int csize = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int ib = blockIdx.x / csize;
+    const int tid = rank * blockDim.x + threadIdx.x;
+    const int nthreads = csize * blockDim.x;
+    const size_t o = (size_t)ib * L.M * L.G;
+    const double* Ti = T + (size_t)ib * L.D * kTabEntries * L.P;
+    const int steps = L.S + kGsLag * (nsweeps - 1);
+    for (int t = 0; t < steps; ++t) {
+        // active hyperplanes of this step: s_k = t - lag*k for sweep k
+        int k_lo = (t - (L.S - 1) + kGsLag - 1) / kGsLag;
+        if (k_lo < 0) k_lo = 0;
+        int k_hi = t / kGsLag;
+        if (k_hi > nsweeps - 1) k_hi = nsweeps - 1;
+        int total = 0;
+        for (int k = k_lo; k <= k_hi; ++k) {
+            const int s = t - kGsLag * k;
+            total += L.hstart[s + 1] - L.hstart[s];
+        }
+        for (int idx = tid; idx < total; idx += nthreads) {
+            int rem = idx, w = -1;
+            for (int k = k_lo; k <= k_hi; ++k) {
+                const int s = t - kGsLag * k;
+                const int h0 = L.hstart[s], cnt = L.hstart[s + 1] - h0;
+                if (rem < cnt) {
+                    w = h0 + rem;
+                    break;
+                }
+                rem -= cnt;
+            }
+            gs_elem<D, LdL2>(L, Ti, coef + o, b + o, x + o, w);
+        }
+        cluster.sync();
+    }
+}
+
+// cross-check variant: one launch per step, no intra-kernel synchronisation
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_gs_step(LevelDev L, const double* __restrict__ T,
+                                                      const double* __restrict__ coef, const double* __restrict__ b,
+                                                      double* x, int nsweeps, int t, const int* done) {
+    if (done && *done) return;
+    const int k = blockIdx.z;
+    const int s = t - kGsLag * k;
+    if (s < 0 || s >= L.S) return;
+    const int h0 = L.hstart[s], cnt = L.hstart[s + 1] - h0;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cnt) return;
+    const size_t o = (size_t)blockIdx.y * L.M * L.G;
+    gs_elem<D, LdL2>(L, T + (size_t)blockIdx.y * L.D * kTabEntries * L.P, coef + o, b + o, x + o, h0 + j);
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+    if (!g_num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+template <int D>
+static void launch_gs_cluster(cudaStream_t s, const LevelDev& L, int B, const double* T, const double* coef,
+                              const double* b, double* x, int nsweeps, const int* done) {
+    // cluster size: as many CTAs per instance as fit on the chip at once, capped by the portable
+    // maximum (8) and by the work of one step (largest hyperplane x sweeps in flight)
+    int maxh = 0;
+    {
+        int n0 = L.N[0], n1 = L.N[1], n2 = L.N[2];
+        // largest hyperplane has at most min over axis pairs of the product of the two other extents
+        int a = n0 * n1, bb = n0 * n2, c = n1 * n2;
+        maxh = a < bb ? a : bb;
+        maxh = maxh < c ? maxh : c;
+    }
+    int want = (maxh * (nsweeps < 5 ? nsweeps : 5) + kGsThreads - 1) / kGsThreads;
+    int fit = num_sms() / (B > 0 ? B : 1);
+    int csize = 1;
+    while (csize * 2 <= 8 && csize * 2 <= fit && csize < want) csize *= 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(B * csize));
+    cfg.blockDim = dim3(kGsThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    note(cudaLaunchKernelEx(&cfg, k_gs_cluster<D>, L, T, coef, b, x, nsweeps, done));
+}
+
+void be_gs(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, const double* b, double* x,
+           int nsweeps, const int* done, int variant) {
+    if (nsweeps <= 0) return;
+    cudaStream_t s = (cudaStream_t)st;
+    if (variant == 0) {
+        if (L.D == 1) launch_gs_cluster<1>(s, L, B, T, coef, b, x, nsweeps, done);
+        else if (L.D == 2) launch_gs_cluster<2>(s, L, B, T, coef, b, x, nsweeps, done);
+        else launch_gs_cluster<3>(s, L, B, T, coef, b, x, nsweeps, done);
+        PDEOP_LAUNCH_CHECK();
+        return;
+    }
+    int maxh = 1;
+    {
+        int a = L.N[0] * L.N[1], bb = L.N[0] * L.N[2], c = L.N[1] * L.N[2];
+        maxh = a < bb ? a : bb;
+        maxh = maxh < c ? maxh : c;
+    }
+    const int steps = L.S + kGsLag * (nsweeps - 1);
+    dim3 grid(cdiv(maxh, kThreads), B, nsweeps);
+    for (int t = 0; t < steps; ++t) {
+        if (L.D == 1) k_gs_step<1><<<grid, kThreads, 0, s>>>(L, T, coef, b, x, nsweeps, t, done);
+        else if (L.D == 2) k_gs_step<2><<<grid, kThreads, 0, s>>>(L, T, coef, b, x, nsweeps, t, done);
+        else k_gs_step<3><<<grid, kThreads, 0, s>>>(L, T, coef, b, x, nsweeps, t, done);
+    }
+    PDEOP_LAUNCH_CHECK();
+}
+
+// =================================================================================================
+// dense coarse operator and gradients
+// =================================================================================================
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_dense(LevelDev L, const double* __restrict__ T,
+                                                    const double* __restrict__ coef, double* __restrict__ Kd) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= L.G) return;
+    const size_t n = (size_t)L.M * L.G;
+    dense_elem<D>(L, T + (size_t)blockIdx.y * L.D * kTabEntries * L.P, coef + (size_t)blockIdx.y * n,
+                  Kd + (size_t)blockIdx.y * n * n, w);
+}
+void be_dense(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, double* Kd) {
+    dim3 grid(cdiv(L.G, kThreads), B);
+    cudaStream_t s = (cudaStream_t)st;
+    if (L.D == 1) k_dense<1><<<grid, kThreads, 0, s>>>(L, T, coef, Kd);
+    else if (L.D == 2) k_dense<2><<<grid, kThreads, 0, s>>>(L, T, coef, Kd);
+    else k_dense<3><<<grid, kThreads, 0, s>>>(L, T, coef, Kd);
+    PDEOP_LAUNCH_CHECK();
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_grads(LevelDev L, const double* __restrict__ coef,
+                                                    const double* __restrict__ rhs_nat, const double* __restrict__ cv,
+                                                    const double* __restrict__ fv, const double* __restrict__ bv,
+                                                    const double* __restrict__ x, const double* __restrict__ dz,
+                                                    double* __restrict__ d_coeffs, double* __restrict__ d_rhs,
+                                                    double* d_cv, double* d_fv, double* d_bv) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= L.G) return;
+    const int ib = blockIdx.y;
+    const size_t n = (size_t)L.M * L.G;
+    const size_t oc = (size_t)ib * L.Ntot * 12, of = (size_t)ib * L.Ftot * 4;
+    grad_elem<D>(L, coef + ib * n, rhs_nat + (size_t)ib * L.G, cv + oc, fv + of, bv + of, x + ib * n, dz + ib * n,
+                 d_coeffs + ib * n, d_rhs + (size_t)ib * L.G, d_cv + oc, d_fv + of, d_bv + of, w);
+}
+__global__ void __launch_bounds__(kThreads) k_grad_init(LevelDev L, const double* __restrict__ dz,
+                                                        double* __restrict__ d_iv) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= L.n_init) return;
+    grad_init_elem(L, dz + (size_t)blockIdx.y * L.M * L.G, d_iv + (size_t)blockIdx.y * L.n_init, k);
+}
+void be_grads(stream_t st, const LevelDev& L, int B, const double* coef, const double* rhs_nat, const double* cv,
+              const double* fv, const double* bv, const double* x, const double* dz, double* d_coeffs, double* d_rhs,
+              double* d_iv, double* d_cv, double* d_fv, double* d_bv) {
+    dim3 grid(cdiv(L.G, kThreads), B);
+    cudaStream_t s = (cudaStream_t)st;
+    if (L.D == 1) k_grads<1><<<grid, kThreads, 0, s>>>(L, coef, rhs_nat, cv, fv, bv, x, dz, d_coeffs, d_rhs, d_cv, d_fv, d_bv);
+    else if (L.D == 2) k_grads<2><<<grid, kThreads, 0, s>>>(L, coef, rhs_nat, cv, fv, bv, x, dz, d_coeffs, d_rhs, d_cv, d_fv, d_bv);
+    else k_grads<3><<<grid, kThreads, 0, s>>>(L, coef, rhs_nat, cv, fv, bv, x, dz, d_coeffs, d_rhs, d_cv, d_fv, d_bv);
+    PDEOP_LAUNCH_CHECK();
+    if (L.n_init > 0) {
+        k_grad_init<<<dim3(cdiv(L.n_init, kThreads), B), kThreads, 0, s>>>(L, dz, d_iv);
+        PDEOP_LAUNCH_CHECK();
+    }
+}
+
+// =================================================================================================
+// Krylov vector kernels
+// =================================================================================================
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// sum of a block's values; result valid in thread 0
+__device__ __forceinline__ double block_sum(double v, double* sm /*[8]*/) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sm[wid] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (wid == 0) {
+        r = lane < (blockDim.x >> 5) ? sm[lane] : 0.0;
+        r = warp_sum(r);
+    }
+    return r;
+}
+
+// deterministic re-summation of nblk block partials by one warp (fixed order for a given nblk)
+__device__ __forceinline__ double warp_sum_partials(const double* __restrict__ p, int nblk) {
+    double a = 0.0;
+    for (int i = threadIdx.x & 31; i < nblk; i += 32) a += p[i];
+    return warp_sum(a);
+}
+
+static inline int reduce_blocks(size_t n) {
+    size_t b = (n + (size_t)kThreads * 4 - 1) / ((size_t)kThreads * 4);
+    if (b < 1) b = 1;
+    if (b > (size_t)kReduceBlocks) b = kReduceBlocks;
+    return (int)b;
+}
+
+// partial[(k0+k)*kReduceBlocks + blk] = sum_i V[(k0+k)*ldv + i] * w[i],  k < K
+template <int K>
+__global__ void __launch_bounds__(kThreads) k_dots(size_t n, const double* __restrict__ V, size_t ldv, int k0,
+                                                   const double* __restrict__ w, double* __restrict__ partial,
+                                                   const int* done) {
+    if (done && *done) return;
+    __shared__ double sm[8];
+    double acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = 0.0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double wi = w[i];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] += V[(size_t)(k0 + k) * ldv + i] * wi;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const double r = block_sum(acc[k], sm);
+        if (threadIdx.x == 0) partial[(size_t)(k0 + k) * kReduceBlocks + blockIdx.x] = r;
+    }
+}
+
+static void launch_dots(cudaStream_t s, size_t n, const double* V, size_t ldv, int nv, const double* w,
+                        double* partial, const int* done) {
+    const int nb = reduce_blocks(n);
+    int k0 = 0;
+    while (k0 < nv) {
+        const int rem = nv - k0;
+        if (rem >= 8) { k_dots<8><<<nb, kThreads, 0, s>>>(n, V, ldv, k0, w, partial, done); k0 += 8; }
+        else if (rem >= 4) { k_dots<4><<<nb, kThreads, 0, s>>>(n, V, ldv, k0, w, partial, done); k0 += 4; }
+        else if (rem >= 2) { k_dots<2><<<nb, kThreads, 0, s>>>(n, V, ldv, k0, w, partial, done); k0 += 2; }
+        else { k_dots<1><<<nb, kThreads, 0, s>>>(n, V, ldv, k0, w, partial, done); k0 += 1; }
+    }
+    PDEOP_LAUNCH_CHECK();
+}
+
+void be_state_reset(stream_t st, FgmresState* s) {
+    note(cudaMemsetAsync(s, 0, sizeof(FgmresState), (cudaStream_t)st));
+}
+
+__global__ void k_begin_final(FgmresState* s, int nblk) {
+    const double v = warp_sum_partials(state_partials(s, 0), nblk);
+    if (threadIdx.x == 0) {
+        s->bnorm = sqrt(v);
+        s->iters = 0;
+        s->rnorm = 0.0;
+        s->done = (s->bnorm == 0.0) ? 1 : 0;   // fgmres.py:76-78
+    }
+}
+void be_fg_begin(stream_t st, size_t n, const double* b, double* x, FgmresState* s) {
+    cudaStream_t cs = (cudaStream_t)st;
+    note(cudaMemsetAsync(x, 0, n * sizeof(double), cs));
+    launch_dots(cs, n, b, 0, 1, b, state_partials(s, 0), nullptr);
+    k_begin_final<<<1, 32, 0, cs>>>(s, reduce_blocks(n));
+    PDEOP_LAUNCH_CHECK();
+}
+
+__global__ void k_resnorm_final(FgmresState* s, int nblk, int maxiter, double atol) {
+    if (s->done) return;
+    const double v = warp_sum_partials(state_partials(s, 0), nblk);
+    if (threadIdx.x == 0) {
+        const double rn = sqrt(v);
+        s->rnorm = rn;
+        if (rn <= atol || s->iters >= maxiter) s->done = 1;   // fgmres.py:134
+        else s->e[0] = rn;
+    }
+}
+void be_fg_resnorm(stream_t st, size_t n, const double* r, FgmresState* s, int maxiter, double atol) {
+    cudaStream_t cs = (cudaStream_t)st;
+    launch_dots(cs, n, r, 0, 1, r, state_partials(s, 0), &s->done);
+    k_resnorm_final<<<1, 32, 0, cs>>>(s, reduce_blocks(n), maxiter, atol);
+    PDEOP_LAUNCH_CHECK();
+}
+
+__global__ void __launch_bounds__(kThreads) k_first(size_t n, const double* __restrict__ r, double* __restrict__ V0,
+                                                    const FgmresState* s) {
+    if (s->done) return;
+    const double rn = s->rnorm;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) V0[i] = r[i] / rn;
+}
+void be_fg_first(stream_t st, size_t n, const double* r, double* V0, FgmresState* s) {
+    k_first<<<reduce_blocks(n), kThreads, 0, (cudaStream_t)st>>>(n, r, V0, s);
+    PDEOP_LAUNCH_CHECK();
+}
+
+// w -= sum_{k<=j} h_k V_k with h_k re-summed from the dot partials; block partials of ||w||^2 -> area 1
+__global__ void __launch_bounds__(kThreads) k_axpy_norm(size_t n, int j, int restart, const double* __restrict__ V,
+                                                        double* __restrict__ w, FgmresState* s, int nblk) {
+    if (s->done) return;
+    __shared__ double h[kMaxRestart];
+    __shared__ double sm[8];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = wid; k <= j; k += (blockDim.x >> 5)) {
+        const double v = warp_sum_partials(state_partials(s, 0) + (size_t)k * kReduceBlocks, nblk);
+        if (lane == 0) {
+            h[k] = v;
+            if (blockIdx.x == 0) s->H[k * restart + j] = v;
+        }
+    }
+    __syncthreads();
+    double acc = 0.0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double wi = w[i];
+        for (int k = 0; k <= j; ++k) wi -= h[k] * V[(size_t)k * n + i];
+        w[i] = wi;
+        acc += wi * wi;
+    }
+    const double r = block_sum(acc, sm);
+    if (threadIdx.x == 0) state_partials(s, 1)[blockIdx.x] = r;
+}
+
+// H[j+1][j] = ||w||, V_{j+1} = w / ||w||
+__global__ void __launch_bounds__(kThreads) k_scale_next(size_t n, int j, int restart, double* __restrict__ V,
+                                                         const double* __restrict__ w, FgmresState* s, int nblk) {
+    if (s->done) return;
+    __shared__ double nn_s;
+    if (threadIdx.x < 32) {
+        const double v = warp_sum_partials(state_partials(s, 1), nblk);
+        if (threadIdx.x == 0) {
+            nn_s = sqrt(v);
+            if (blockIdx.x == 0) s->H[(j + 1) * restart + j] = nn_s;
+        }
+    }
+    __syncthreads();
+    if (j + 1 >= restart) return;
+    const double nn = nn_s;
+    double* vn = V + (size_t)(j + 1) * n;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) vn[i] = w[i] / nn;
+}
+
+void be_fg_cgs(stream_t st, size_t n, int j, int restart, double* V, double* w, FgmresState* s) {
+    cudaStream_t cs = (cudaStream_t)st;
+    const int nb = reduce_blocks(n);
+    launch_dots(cs, n, V, n, j + 1, w, state_partials(s, 0), &s->done);
+    k_axpy_norm<<<nb, kThreads, 0, cs>>>(n, j, restart, V, w, s, nb);
+    k_scale_next<<<(j + 1 < restart) ? nb : 1, kThreads, 0, cs>>>(n, j, restart, V, w, s, nb);
+    PDEOP_LAUNCH_CHECK();
+}
+
+__global__ void k_lstsq(FgmresState* s, int restart) {
+    if (s->done) return;
+    if (threadIdx.x == 0) hessenberg_lstsq(s->H, s->e, restart, s->y);
+}
+__global__ void __launch_bounds__(kThreads) k_update(size_t n, int restart, const double* __restrict__ Z,
+                                                     double* __restrict__ x, FgmresState* s) {
+    if (s->done) return;
+    __shared__ double y[kMaxRestart];
+    if (threadIdx.x < restart) y[threadIdx.x] = s->y[threadIdx.x];
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double xi = x[i];
+        for (int k = 0; k < restart; ++k) xi += y[k] * Z[(size_t)k * n + i];
+        x[i] = xi;
+    }
+}
+__global__ void k_iters_add(FgmresState* s, int restart) {
+    if (s->done) return;
+    s->iters += restart;
+}
+void be_fg_update(stream_t st, size_t n, int restart, const double* Z, double* x, FgmresState* s) {
+    cudaStream_t cs = (cudaStream_t)st;
+    k_lstsq<<<1, 32, 0, cs>>>(s, restart);
+    k_update<<<reduce_blocks(n), kThreads, 0, cs>>>(n, restart, Z, x, s);
+    k_iters_add<<<1, 1, 0, cs>>>(s, restart);
+    PDEOP_LAUNCH_CHECK();
+}
+
+__global__ void k_info(const FgmresState* s, double* info4) {
+    info4[0] = (double)s->iters;
+    info4[1] = s->rnorm;
+    info4[2] = s->bnorm;
+    info4[3] = (double)s->chol_info;
+}
+void be_fg_info(stream_t st, const FgmresState* s, double* info4) {
+    k_info<<<1, 1, 0, (cudaStream_t)st>>>(s, info4);
+    PDEOP_LAUNCH_CHECK();
+}
+void be_fg_hess(stream_t st, const FgmresState* s, int restart, double* hess_out) {
+    note(cudaMemcpyAsync(hess_out, s->H, sizeof(double) * (restart + 1) * restart, cudaMemcpyDeviceToDevice,
+                         (cudaStream_t)st));
+}
+
+// =================================================================================================
+// Batched dense Cholesky (lower, in place, row-major n x n per instance).
+// Two-level blocked right-looking: outer panels of kOuter columns, inner steps of kInner columns
+// (diag factor in shared memory, row-wise triangular solve of the panel, SYRK of the rest of the outer
+// panel), then one deep SYRK of the trailing matrix per outer panel (depth kOuter => compute-bound).
+// =================================================================================================
+constexpr int kInner = 32;
+constexpr int kOuter = 256;
+
+__global__ void __launch_bounds__(256) k_chol_diag(int n, double* A, size_t strideA, int k0, int nb,
+                                                   FgmresState* st) {
+    __shared__ double a[kInner][kInner + 1];
+    double* Ab = A + (size_t)blockIdx.x * strideA;
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
+        const int i = idx / nb, j = idx % nb;
+        a[i][j] = (j <= i) ? Ab[(size_t)(k0 + i) * n + k0 + j] : 0.0;
+    }
+    __syncthreads();
+    for (int j = 0; j < nb; ++j) {
+        if (tid == 0) {
+            double d = a[j][j];
+            if (!(d > 0.0)) {
+                atomicCAS(&st->chol_info, 0, k0 + j + 1);
+                d = 1.0;
+            }
+            a[j][j] = sqrt(d);
+        }
+        __syncthreads();
+        const double djj = a[j][j];
+        for (int i = j + 1 + tid; i < nb; i += blockDim.x) a[i][j] /= djj;
+        __syncthreads();
+        const int m = nb - j - 1;
+        for (int idx = tid; idx < m * m; idx += blockDim.x) {
+            const int i = j + 1 + idx / m, k = j + 1 + idx % m;
+            if (k <= i) a[i][k] -= a[i][j] * a[k][j];
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
+        const int i = idx / nb, j = idx % nb;
+        if (j <= i) Ab[(size_t)(k0 + i) * n + k0 + j] = a[i][j];
+    }
+}
+
+// rows r in [k0+nb, n):  A[r, k0:k0+nb] <- A[r, k0:k0+nb] * L11^-T
+__global__ void __launch_bounds__(128) k_chol_trsm(int n, double* A, size_t strideA, int k0, int nb) {
+    __shared__ double l[kInner][kInner + 1];
+    double* Ab = A + (size_t)blockIdx.y * strideA;
+    for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) {
+        const int i = idx / nb, j = idx % nb;
+        l[i][j] = Ab[(size_t)(k0 + i) * n + k0 + j];
+    }
+    __syncthreads();
+    const int r = k0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    double* row = Ab + (size_t)r * n + k0;
+    double v[kInner];
+#pragma unroll
+    for (int j = 0; j < kInner; ++j) v[j] = j < nb ? row[j] : 0.0;
+#pragma unroll
+    for (int j = 0; j < kInner; ++j) {
+        if (j < nb) {
+            double s = v[j];
+#pragma unroll
+            for (int t = 0; t < j; ++t) s -= v[t] * l[j][t];
+            v[j] = s / l[j][j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kInner; ++j)
+        if (j < nb) row[j] = v[j];
+}
+
+// C[i][j] -= sum_{t in [p0,p1)} A[i][t] A[j][t]   for i in [r0,n), j in [c0,c1), i >= j
+__global__ void __launch_bounds__(256) k_syrk(int n, double* A, size_t strideA, int r0, int c0, int c1, int p0,
+                                              int p1) {
+    const int i0 = r0 + blockIdx.x * 64, j0 = c0 + blockIdx.y * 64;
+    if (i0 + 63 < j0) return;
+    __shared__ double As[16][64 + 2], Bs[16][64 + 2];
+    double* Ab = A + (size_t)blockIdx.z * strideA;
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int lrow = tid >> 2, lk = (tid & 3) * 4;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    for (int kk = p0; kk < p1; kk += 16) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = kk + lk + q;
+            const int ia = i0 + lrow, jb = j0 + lrow;
+            As[lk + q][lrow] = (ia < n && k < p1) ? Ab[(size_t)ia * n + k] : 0.0;
+            Bs[lk + q][lrow] = (jb < c1 && k < p1) ? Ab[(size_t)jb * n + k] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            double av[4], bv[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) av[a] = As[k][ty * 4 + a];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) bv[b] = Bs[k][tx * 4 + b];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] += av[a] * bv[b];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int i = i0 + ty * 4 + a, j = j0 + tx * 4 + b;
+            if (i < n && j < c1 && i >= j) Ab[(size_t)i * n + j] -= acc[a][b];
+        }
+}
+
+static void launch_syrk(cudaStream_t s, int B, int n, double* A, int r0, int c0, int c1, int p0, int p1) {
+    if (r0 >= n || c0 >= c1 || p0 >= p1) return;
+    dim3 grid(cdiv(n - r0, 64), cdiv(c1 - c0, 64), B);
+    k_syrk<<<grid, 256, 0, s>>>(n, A, (size_t)n * n, r0, c0, c1, p0, p1);
+}
+
+void be_cholesky(stream_t st, int B, int n, double* Kd, FgmresState* state) {
+    cudaStream_t s = (cudaStream_t)st;
+    const size_t strideA = (size_t)n * n;
+    for (int K0 = 0; K0 < n; K0 += kOuter) {
+        const int K1 = K0 + kOuter < n ? K0 + kOuter : n;
+        for (int k0 = K0; k0 < K1; k0 += kInner) {
+            const int nb = k0 + kInner < K1 ? kInner : K1 - k0;
+            k_chol_diag<<<B, 256, 0, s>>>(n, Kd, strideA, k0, nb, state);
+            if (k0 + nb < n) {
+                k_chol_trsm<<<dim3(cdiv(n - k0 - nb, 128), B), 128, 0, s>>>(n, Kd, strideA, k0, nb);
+                // rest of the outer panel: columns [k0+nb, K1)
+                launch_syrk(s, B, n, Kd, k0 + nb, k0 + nb, K1, k0, k0 + nb);
+            }
+        }
+        // trailing matrix: columns [K1, n), depth kOuter
+        launch_syrk(s, B, n, Kd, K1, K1, n, K0, K1);
+    }
+    PDEOP_LAUNCH_CHECK();
+}
+
+// =================================================================================================
+// Blocked triangular solves  out = L^-T L^-1 rhs  (HBM-bound on L: each triangle is read once).
+// Block rows of kSolveBlk; per block: a GEMV with everything already solved + a small triangular solve.
+// =================================================================================================
+constexpr int kSolveBlk = 256;
+constexpr int kSolveSub = 64;
+
+// t[i] = r[i] - sum_{c<k0} L[i][c] y[c]   for rows i in [k0, k0+w): one warp per row
+__global__ void __launch_bounds__(256) k_fwd_gemv(int n, const double* __restrict__ Lf, size_t strideL, int k0, int w,
+                                                  const double* __restrict__ r, const double* __restrict__ y,
+                                                  double* __restrict__ t, const int* done) {
+    if (done && *done) return;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= w) return;
+    const int lane = threadIdx.x & 31;
+    const int ib = blockIdx.y;
+    const double* Lr = Lf + (size_t)ib * strideL + (size_t)(k0 + row) * n;
+    const double* yb = y + (size_t)ib * n;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int c = lane;
+    for (; c + 96 < k0; c += 128) {
+        a0 += Lr[c] * yb[c];
+        a1 += Lr[c + 32] * yb[c + 32];
+        a2 += Lr[c + 64] * yb[c + 64];
+        a3 += Lr[c + 96] * yb[c + 96];
+    }
+    for (; c < k0; c += 32) a0 += Lr[c] * yb[c];
+    const double a = warp_sum((a0 + a1) + (a2 + a3));
+    if (lane == 0) t[(size_t)ib * n + k0 + row] = r[(size_t)ib * n + k0 + row] - a;
+}
+
+// solve L_kk y_k = t_k in place (t -> y) for the block [k0, k0+w): one CTA per instance
+__global__ void __launch_bounds__(256) k_fwd_diag(int n, const double* __restrict__ Lf, size_t strideL, int k0, int w,
+                                                  const double* __restrict__ t, double* __restrict__ y,
+                                                  const int* done) {
+    if (done && *done) return;
+    __shared__ double Ls[kSolveSub][kSolveSub + 1];
+    __shared__ double ys[kSolveBlk];
+    const int tid = threadIdx.x;
+    const int ib = blockIdx.x;
+    const double* Lb = Lf + (size_t)ib * strideL;
+    for (int i = tid; i < w; i += blockDim.x) ys[i] = t[(size_t)ib * n + k0 + i];
+    for (int s0 = 0; s0 < w; s0 += kSolveSub) {
+        const int sw = s0 + kSolveSub < w ? kSolveSub : w - s0;
+        __syncthreads();
+        for (int idx = tid; idx < sw * sw; idx += blockDim.x) {
+            const int i = idx / sw, j = idx % sw;
+            Ls[i][j] = Lb[(size_t)(k0 + s0 + i) * n + k0 + s0 + j];
+        }
+        __syncthreads();
+        for (int j = 0; j < sw; ++j) {
+            if (tid == 0) ys[s0 + j] /= Ls[j][j];
+            __syncthreads();
+            const double yj = ys[s0 + j];
+            for (int i = j + 1 + tid; i < sw; i += blockDim.x) ys[s0 + i] -= Ls[i][j] * yj;
+            __syncthreads();
+        }
+        // rows of this block below the sub-block
+        for (int i = s0 + sw + tid; i < w; i += blockDim.x) {
+            const double* Lr = Lb + (size_t)(k0 + i) * n + k0 + s0;
+            double a = 0.0;
+            for (int j = 0; j < sw; ++j) a += Lr[j] * ys[s0 + j];
+            ys[i] -= a;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < w; i += blockDim.x) y[(size_t)ib * n + k0 + i] = ys[i];
+}
+
+// solve L_kk^T z_k = y_k in place for the block [k0, k0+w)
+__global__ void __launch_bounds__(256) k_bwd_diag(int n, const double* __restrict__ Lf, size_t strideL, int k0, int w,
+                                                  double* __restrict__ y, const int* done) {
+    if (done && *done) return;
+    __shared__ double Ls[kSolveSub][kSolveSub + 1];
+    __shared__ double zs[kSolveBlk];
+    const int tid = threadIdx.x;
+    const int ib = blockIdx.x;
+    const double* Lb = Lf + (size_t)ib * strideL;
+    for (int i = tid; i < w; i += blockDim.x) zs[i] = y[(size_t)ib * n + k0 + i];
+    const int nsub = (w + kSolveSub - 1) / kSolveSub;
+    for (int sb = nsub - 1; sb >= 0; --sb) {
+        const int s0 = sb * kSolveSub;
+        const int sw = s0 + kSolveSub < w ? kSolveSub : w - s0;
+        __syncthreads();
+        for (int idx = tid; idx < sw * sw; idx += blockDim.x) {
+            const int i = idx / sw, j = idx % sw;
+            Ls[i][j] = Lb[(size_t)(k0 + s0 + i) * n + k0 + s0 + j];
+        }
+        __syncthreads();
+        for (int j = sw - 1; j >= 0; --j) {
+            if (tid == 0) zs[s0 + j] /= Ls[j][j];
+            __syncthreads();
+            const double zj = zs[s0 + j];
+            for (int i = tid; i < j; i += blockDim.x) zs[s0 + i] -= Ls[j][i] * zj;
+            __syncthreads();
+        }
+        // columns of this block left of the sub-block: z[c] -= sum_j L[s0+j][c] z[s0+j]
+        for (int c = tid; c < s0; c += blockDim.x) {
+            double a = 0.0;
+            for (int j = 0; j < sw; ++j) a += Lb[(size_t)(k0 + s0 + j) * n + k0 + c] * zs[s0 + j];
+            zs[c] -= a;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < w; i += blockDim.x) y[(size_t)ib * n + k0 + i] = zs[i];
+}
+
+// y[c] -= sum_{r in [k0,k0+w)} L[r][c] z[r]  for c < k0: one thread per column (coalesced along rows of L)
+__global__ void __launch_bounds__(256) k_bwd_update(int n, const double* __restrict__ Lf, size_t strideL, int k0,
+                                                    int w, double* __restrict__ y, const int* done) {
+    if (done && *done) return;
+    __shared__ double zs[kSolveBlk];
+    const int ib = blockIdx.y;
+    double* yb = y + (size_t)ib * n;
+    for (int i = threadIdx.x; i < w; i += blockDim.x) zs[i] = yb[k0 + i];
+    __syncthreads();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= k0) return;
+    const double* Lc = Lf + (size_t)ib * strideL + (size_t)k0 * n + c;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int r = 0;
+    for (; r + 3 < w; r += 4) {
+        a0 += Lc[(size_t)r * n] * zs[r];
+        a1 += Lc[(size_t)(r + 1) * n] * zs[r + 1];
+        a2 += Lc[(size_t)(r + 2) * n] * zs[r + 2];
+        a3 += Lc[(size_t)(r + 3) * n] * zs[r + 3];
+    }
+    for (; r < w; ++r) a0 += Lc[(size_t)r * n] * zs[r];
+    yb[c] -= (a0 + a1) + (a2 + a3);
+}
+
+void be_chol_solve(stream_t st, int B, int n, const double* Lf, const double* rhs, double* out, double* work,
+                   const int* done) {
+    cudaStream_t s = (cudaStream_t)st;
+    const size_t strideL = (size_t)n * n;
+    // forward: y (in `out`) = L^-1 rhs
+    for (int k0 = 0; k0 < n; k0 += kSolveBlk) {
+        const int w = k0 + kSolveBlk < n ? kSolveBlk : n - k0;
+        const double* tsrc = rhs;
+        if (k0 > 0) {
+            k_fwd_gemv<<<dim3(cdiv(w, 8), B), 256, 0, s>>>(n, Lf, strideL, k0, w, rhs, out, work, done);
+            tsrc = work;
+        }
+        k_fwd_diag<<<B, 256, 0, s>>>(n, Lf, strideL, k0, w, tsrc, out, done);
+    }
+    // backward: out = L^-T y, in place
+    const int nblk = (n + kSolveBlk - 1) / kSolveBlk;
+    for (int kb = nblk - 1; kb >= 0; --kb) {
+        const int k0 = kb * kSolveBlk;
+        const int w = k0 + kSolveBlk < n ? kSolveBlk : n - k0;
+        k_bwd_diag<<<B, 256, 0, s>>>(n, Lf, strideL, k0, w, out, done);
+        if (k0 > 0) k_bwd_update<<<dim3(cdiv(k0, 256), B), 256, 0, s>>>(n, Lf, strideL, k0, w, out, done);
+    }
+    PDEOP_LAUNCH_CHECK();
+}
+
+}  // namespace pdeop

@@ -13,6 +13,21 @@
 #pragma once
 #include "pdeop_common.h"
 
+// Load policy for vectors that other thread blocks of the SAME kernel may be writing (the in-place
+// Gauss-Seidel iterate): ld.global.cg reads at the L2 coherence point.  Everything else uses LdPlain.
+struct LdPlain {
+    static PDEOP_HD double ld(const double* p) { return *p; }
+};
+struct LdL2 {
+    static PDEOP_HD double ld(const double* p) {
+#if defined(__CUDA_ARCH__)
+        return __ldcg(p);
+#else
+        return *p;
+#endif
+    }
+};
+
 #ifndef PDEOP_ATOMIC_ADD
 #if defined(__CUDA_ARCH__)
 #define PDEOP_ATOMIC_ADD(p, v) atomicAdd((p), (v))
@@ -131,8 +146,8 @@ PDEOP_HD int neighbor_pos(const LevelDev& L, int s, int i0, int i1, int o) {
 // acc[m] = sum over OFF-POINT couplings  K[(g,m),(g',m')] x[g',m'],  g' = g + o e_a, o in [-4,4]\{0}
 // T: instance tables [D][30][P];  x: instance vector [M][G]
 // ------------------------------------------------------------------------------------------------
-template <int D>
-PDEOP_HD void k_neighbors(const LevelDev& L, const double* __restrict__ T, const double* __restrict__ x, int i0,
+template <int D, class LD>
+PDEOP_HD void k_neighbors(const LevelDev& L, const double* __restrict__ T, const double* x, int i0,
                           int i1, int i2, double acc[1 + 2 * D]) {
     const int G = L.G, P = L.P;
     const int s = i0 + i1 + i2;
@@ -141,8 +156,6 @@ PDEOP_HD void k_neighbors(const LevelDev& L, const double* __restrict__ T, const
     for (int m = 0; m < 1 + 2 * D; ++m) acc[m] = 0.0;
 #pragma unroll
     for (int a = 0; a < D; ++a) {
-        constexpr int kDummy = 0;
-        (void)kDummy;
         const int ax = 3 - D + a;
         const int n = L.N[ax];
         const int i = idx[ax];
@@ -157,9 +170,9 @@ PDEOP_HD void k_neighbors(const LevelDev& L, const double* __restrict__ T, const
             if (ax == 2) wn = neighbor_pos<2>(L, s, i0, i1, o);
             else if (ax == 1) wn = neighbor_pos<1>(L, s, i0, i1, o);
             else wn = neighbor_pos<0>(L, s, i0, i1, o);
-            const double un = x[wn];
-            const double pn = x[(size_t)(1 + a) * G + wn];
-            const double qn = x[(size_t)(1 + D + a) * G + wn];
+            const double un = LD::ld(x + wn);
+            const double pn = LD::ld(x + (size_t)(1 + a) * G + wn);
+            const double qn = LD::ld(x + (size_t)(1 + D + a) * G + wn);
             au += Ta[(T_UU + o + 4) * P] * un + Ta[(T_UP - o + 4) * P + o] * pn + Ta[(T_UQ - o + 4) * P + o] * qn;
             ap += Ta[(T_UP + o + 4) * P] * un;
             aq += Ta[(T_UQ + o + 4) * P] * un;
@@ -216,7 +229,7 @@ PDEOP_HD void apply_k_elem(const LevelDev& L, const double* __restrict__ T, cons
     unpack_coord(L.coord[w], i0, i1, i2);
     const int flags = L.flags[w];
     double acc[M];
-    k_neighbors<D>(L, T, x, i0, i1, i2, acc);
+    k_neighbors<D, LdPlain>(L, T, x, i0, i1, i2, acc);
     PointLocal<D> pl;
     load_local<D>(L, T, coef, w, i0, i1, i2, flags, pl);
     double xl[M];
@@ -245,7 +258,7 @@ PDEOP_HD void apply_k_elem(const LevelDev& L, const double* __restrict__ T, cons
 
 // One lexicographic Gauss-Seidel update of the M unknowns of point w (channel order 0..M-1):
 //   x_j <- (b_j - sum_{k != j} K_jk x_k) / K_jj   with already-updated values for k < j.
-template <int D>
+template <int D, class LD>
 PDEOP_HD void gs_elem(const LevelDev& L, const double* __restrict__ T, const double* __restrict__ coef,
                       const double* __restrict__ b, double* x, int w) {
     constexpr int M = 1 + 2 * D;
@@ -254,13 +267,13 @@ PDEOP_HD void gs_elem(const LevelDev& L, const double* __restrict__ T, const dou
     unpack_coord(L.coord[w], i0, i1, i2);
     const int flags = L.flags[w];
     double acc[M];
-    k_neighbors<D>(L, T, x, i0, i1, i2, acc);
+    k_neighbors<D, LD>(L, T, x, i0, i1, i2, acc);
     PointLocal<D> pl;
     load_local<D>(L, T, coef, w, i0, i1, i2, flags, pl);
     double xl[M], r[M];
 #pragma unroll
     for (int m = 0; m < M; ++m) {
-        xl[m] = x[(size_t)m * G + w];
+        xl[m] = LD::ld(x + (size_t)m * G + w);
         r[m] = b[(size_t)m * G + w] - acc[m];
     }
 #pragma unroll

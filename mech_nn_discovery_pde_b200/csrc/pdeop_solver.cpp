@@ -197,7 +197,7 @@ struct Scratch {
     size_t n0;
 };
 
-static size_t state_doubles() { return (sizeof(FgmresState) + 255) / 256 * 32; }
+static size_t state_doubles() { return kStateAreaDoubles; }
 
 static size_t scratch_doubles(const pdeop_plan* pl, int restart) {
     const LevelDev& L0 = pl->lev[0].dev;

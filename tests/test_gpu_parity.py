@@ -1,0 +1,186 @@
+"""GPU parity tests: the CUDA path (csrc/libpdeop.so, called through the C ABI) against
+  (1) golden vectors produced by the unmodified reference (tests/golden),
+  (2) the CPU oracle on fresh seeded inputs,
+  (3) size-independent properties at BASELINE-sized grids.
+Tolerances follow BASELINE.json north_star: 1e-8 relative in fp64, FGMRES iteration counts equal."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from mech_nn_discovery_pde_b200 import _lib
+from oracle import pde_oracle as O
+from oracle.cases import IV_LISTS, make_inputs
+from tests.helpers import GOLDEN, StageRunner, load_layer_case, rel, run_layer_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return _lib.get_library()
+
+
+STAGE_CASES = ["mg_2d_16x16_g2", "mg_2d_32x32_g3", "mg_3d_8x16x16_g2_nodsf"]
+
+
+@pytest.mark.parametrize("name", STAGE_CASES)
+def test_stages_vs_reference(lib, name):
+    s = np.load(os.path.join(GOLDEN, f"stages_{name}.npz"))
+    z, dims, steps = load_layer_case(name)
+    B = int(z["bs"])
+    iv = IV_LISTS[str(z["iv_name"])]
+    sr = StageRunner(lib, "cuda:0", dims, iv, B, int(z["n_grid"]), bool(z["dsf"]), z["coeffs"], steps)
+    assert int(sr.info[3].item()) == 0
+    assert rel(sr.stage(_lib.STAGE_ATB, 0, z["rhs"], z["iv_rhs"]), s["Atb"]) < 1e-13
+    assert rel(sr.stage(_lib.STAGE_APPLY_K, 0, s["v"]), s["Kv"]) < 1e-13
+    assert rel(sr.stage(_lib.STAGE_GS, 0, s["v"], s["x0"], count=1), s["gs1"]) < 1e-12
+    gs3 = sr.stage(_lib.STAGE_GS, 0, s["v"], s["x0"], count=3)
+    assert rel(gs3, s["gs3"]) < 1e-12
+    # the persistent cluster kernel and the launch-per-hyperplane kernel are the same arithmetic: same bits
+    gs3b = sr.stage(_lib.STAGE_GS, 0, s["v"], s["x0"], count=3, gs_variant=1)
+    assert np.array_equal(gs3, gs3b)
+    gs5 = sr.stage(_lib.STAGE_GS, 0, s["v"], s["x0"], count=5)
+    gs5b = sr.stage(_lib.STAGE_GS, 0, s["v"], s["x0"], count=5, gs_variant=1)
+    assert np.array_equal(gs5, gs5b)
+    assert rel(sr.stage(_lib.STAGE_RESTRICT, 0, s["v"], out_level=1), s["restrict"]) < 1e-13
+    assert rel(sr.stage(_lib.STAGE_PROLONG, 1, s["vc"], out_level=0), s["prolong"]) < 1e-13
+    assert rel(sr.stage(_lib.STAGE_VCYCLE, 0, s["v"]), s["vcycle"]) < 1e-9
+    if "v1" in s.files:
+        assert rel(sr.stage(_lib.STAGE_APPLY_K, 1, s["v1"]), s["K1v1"]) < 1e-13
+    # coarsest dense solve against the oracle's factorisation of the same operator
+    mg = O.mg_setup(dims, iv, z["coeffs"], z["rhs"], z["iv_rhs"], steps, int(z["n_grid"]), bool(z["dsf"]))
+    lc = int(z["n_grid"]) - 1
+    nc = sr.level_n(lc)
+    rng = np.random.default_rng(5)
+    rc = rng.standard_normal(B * nc)
+    got = sr.stage(_lib.STAGE_COARSE_SOLVE, lc, rc)
+    assert rel(got, O.solve_coarsest(mg, rc)) < 1e-7
+    Kc = mg.K_list[-1]
+    back = np.einsum("bij,bj->bi", Kc, got.reshape(B, nc)).reshape(-1)
+    assert rel(back, rc) < 1e-9
+
+
+LAYER_CASES = ["dense_1d_24", "dense_2d_8x10", "dense_2d_12x12_sine_uniform", "dense_3d_8x8x8", "mg_2d_16x16_g2",
+               "mg_2d_32x32_g3", "mg_2d_16x32_g2_nodsf", "mg_3d_8x16x16_g2_nodsf", "mg_3d_16x16x16_g2"]
+
+
+def _check_layer(z, out):
+    dense = str(z["kind"]) == "dense"
+    tol_x, tol_g = (1e-8, 2e-7) if dense else (1e-8, 1e-8)
+    assert rel(out["u"], z["u"]) < tol_x
+    assert rel(out["d_coeffs"], z["d_coeffs"]) < tol_g
+    assert rel(out["d_rhs"], z["d_rhs"]) < tol_g
+    assert rel(out["d_iv_rhs"], z["d_iv_rhs"]) < tol_g
+    for c in range(len(out["d_steps"])):
+        assert rel(out["d_steps"][c], z[f"d_steps{c}"]) < max(tol_g, 1e-7)
+    if not dense:
+        info = z["info"]
+        assert abs(int(out["info_fwd"][0]) - int(info[0, 0])) <= 1 and abs(int(out["info_bwd"][0]) - int(info[1, 0])) <= 1
+        assert abs(out["info_fwd"][1] - info[0, 1]) <= 1e-6 * info[0, 1]
+        assert abs(out["info_bwd"][1] - info[1, 1]) <= 1e-6 * info[1, 1]
+
+
+@pytest.mark.parametrize("name", LAYER_CASES)
+def test_layer_vs_reference(lib, name):
+    z, out = run_layer_case(lib, "cuda:0", name)
+    _check_layer(z, out)
+
+
+def test_layer_vs_oracle_seeded(lib):
+    """Fresh seeded inputs (not in the golden set): CUDA layer against the CPU oracle run here."""
+    from mech_nn_discovery_pde_b200 import MultigridLayer
+    dims, B, n_grid, dsf = (16, 24), 3, 2, True
+    iv = IV_LISTS["burgers"]
+    st = O.build_structure(dims, iv)
+    inp = make_inputs(dims, B, st.n_init, seed=777)
+    g_out = inp["loss_w"].reshape(B, -1)
+    ref = O.mg_layer(dims, iv, inp["coeffs"], inp["rhs"], inp["iv_rhs"], inp["steps"], n_grid, dsf, grad_out=g_out)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
+    layer = MultigridLayer(bs=B, coord_dims=dims, order=2, n_ind_dim=1, n_iv=1, n_grid=n_grid, downsample_first=dsf,
+                           init_index_mi_list=iv, n_iv_steps=1)
+    coeffs = t(inp["coeffs"]).requires_grad_(True)
+    rhs = t(inp["rhs"]).requires_grad_(True)
+    ivr = t(inp["iv_rhs"]).requires_grad_(True)
+    steps = [t(s).requires_grad_(True) for s in inp["steps"]]
+    u0, u, _ = layer(coeffs, rhs, ivr, list(steps))
+    (u * t(inp["loss_w"]).reshape(u.shape)).sum().backward()
+    assert rel(u.detach().cpu().numpy().reshape(B, -1), ref.x) < 1e-8
+    assert rel(coeffs.grad.cpu().numpy(), ref.d_coeffs) < 1e-8
+    assert rel(rhs.grad.cpu().numpy(), ref.d_rhs) < 1e-8
+    assert rel(ivr.grad.cpu().numpy(), ref.d_iv_rhs) < 1e-8
+    for c in range(len(dims)):
+        assert rel(steps[c].grad.cpu().numpy(), ref.d_steps[c]) < 1e-7
+    f, b = layer.solver_info()
+    assert f[0] == ref.info_fwd[0] and b[0] == ref.info_bwd[0]
+
+
+def test_cuda_vs_emulator_medium(lib):
+    """Same per-element arithmetic on GPU and in the host emulator at a size the oracle would need minutes for."""
+    from tests.emu.emu_lib import emu_library
+    dims, B, n_grid, dsf = (8, 32, 32), 2, 3, False
+    iv = IV_LISTS["gl"]
+    st = O.build_structure(dims, iv)
+    inp = make_inputs(dims, B, st.n_init, seed=99)
+    rng = np.random.default_rng(3)
+    n = B * st.n
+    v, x0 = rng.standard_normal(n), rng.standard_normal(n)
+    outs = []
+    for lb, dev in ((lib, "cuda:0"), (emu_library(), "cpu")):
+        sr = StageRunner(lb, dev, dims, iv, B, n_grid, dsf, inp["coeffs"], inp["steps"])
+        outs.append(dict(k=sr.stage(_lib.STAGE_APPLY_K, 0, v), gs=sr.stage(_lib.STAGE_GS, 0, v, x0, count=5),
+                         vc=sr.stage(_lib.STAGE_VCYCLE, 0, v)))
+    assert rel(outs[0]["k"], outs[1]["k"]) < 1e-14
+    assert rel(outs[0]["gs"], outs[1]["gs"]) < 1e-13
+    assert rel(outs[0]["vc"], outs[1]["vc"]) < 1e-9
+
+
+def test_full_size_properties(lib):
+    """BASELINE-sized Ginzburg-Landau grid (32x64x64): properties that hold at any size."""
+    dims, B, n_grid, dsf = (32, 64, 64), 2, 3, True
+    iv = IV_LISTS["gl"]
+    st = O.build_structure((8, 8, 8), iv)  # only to learn M; inputs are made below
+    G = int(np.prod(dims))
+    M = 7
+    g = torch.Generator().manual_seed(5)
+    coeffs = torch.zeros(B, G, M, dtype=torch.float64)
+    coeffs[..., 0] = 0.1 * torch.randn(B, G, generator=g, dtype=torch.float64)
+    coeffs[..., 1] = 1.0
+    coeffs[..., 5] = -1.0
+    coeffs[..., 6] = -1.0
+    steps = [np.full((B, n - 1), h) for n, h in zip(dims, (0.1, 0.3906, 0.3906))]
+    sr = StageRunner(lib, "cuda:0", dims, iv, B, n_grid, dsf, coeffs.numpy(), steps)
+    assert int(sr.info[3].item()) == 0
+    n = B * G * M
+    rng = np.random.default_rng(11)
+    x, y = rng.standard_normal(n), rng.standard_normal(n)
+    Kx, Ky = sr.stage(_lib.STAGE_APPLY_K, 0, x), sr.stage(_lib.STAGE_APPLY_K, 0, y)
+    Kxy = sr.stage(_lib.STAGE_APPLY_K, 0, 2.0 * x - 3.0 * y)
+    assert rel(Kxy, 2.0 * Kx - 3.0 * Ky) < 1e-12                       # linearity
+    assert abs(x @ Ky - y @ Kx) < 1e-10 * abs(x @ Ky)                  # symmetry
+    assert x @ Kx > 0                                                  # positive definite
+    # Gauss-Seidel on an SPD operator decreases the energy 1/2 x'Kx - b'x monotonically
+    b = Ky
+    cur = np.zeros(n)
+    prev = 0.0
+    for _ in range(3):
+        cur = sr.stage(_lib.STAGE_GS, 0, b, cur, count=1)
+        e = 0.5 * cur @ sr.stage(_lib.STAGE_APPLY_K, 0, cur) - b @ cur
+        assert e < prev
+        prev = e
+    # 5 pipelined sweeps == 5 single sweeps, bit for bit; cluster kernel == per-hyperplane kernel
+    a5 = sr.stage(_lib.STAGE_GS, 0, b, np.zeros(n), count=5)
+    c = np.zeros(n)
+    for _ in range(5):
+        c = sr.stage(_lib.STAGE_GS, 0, b, c, count=1)
+    assert np.array_equal(a5, c)
+    assert np.array_equal(a5, sr.stage(_lib.STAGE_GS, 0, b, np.zeros(n), count=5, gs_variant=1))
+    # grid transfer reproduces constants exactly
+    ones = np.ones(n)
+    assert np.abs(sr.stage(_lib.STAGE_RESTRICT, 0, ones, out_level=1) - 1.0).max() < 1e-14
+    # the V-cycle is a contraction for the residual of K z = b
+    z = sr.stage(_lib.STAGE_VCYCLE, 0, b)
+    assert np.linalg.norm(b - sr.stage(_lib.STAGE_APPLY_K, 0, z)) < 0.9 * np.linalg.norm(b)
