@@ -125,6 +125,15 @@ int pdeop_stage(pdeop_plan* plan, const pdeop_solver_cfg* cfg, int stage, int le
 int pdeop_fgmres(pdeop_plan* plan, const pdeop_solver_cfg* cfg, int back, const double* b, double* x_out,
                  double* info_out, double* hess_out, void* persist, void* scratch, void* stream);
 
+/* Instrumentation (bench.py): per-category device time measured with events recorded on the launching
+ * stream around each kernel group, and the number of kernels this library has launched.
+ * Categories: 0 GS fine level, 1 GS coarser levels, 2 K-apply/residual fine, 3 K-apply coarser, 4 grid
+ * transfer, 5 coarsest triangular solves, 6 coarsest factorisation, 7 Krylov vector kernels, 8 set-up,
+ * 9 gradients, 10 layout conversion. */
+void pdeop_profile_enable(int on);
+int pdeop_profile_collect(double* ms_per_category, long long* count_per_category, int ncat);
+long long pdeop_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,8 +30,11 @@ class SolverCfg(ctypes.Structure):
 EXPORTS = [
     "pdeop_plan_create", "pdeop_plan_destroy", "pdeop_plan_query", "pdeop_last_error", "pdeop_backend_name",
     "pdeop_mg_forward", "pdeop_mg_backward", "pdeop_dense_forward", "pdeop_dense_backward", "pdeop_mg_setup",
-    "pdeop_stage", "pdeop_fgmres",
+    "pdeop_stage", "pdeop_fgmres", "pdeop_profile_enable", "pdeop_profile_collect", "pdeop_launch_count",
 ]
+
+PROFILE_CATEGORIES = ["gs_fine", "gs_coarse", "apply_fine", "apply_coarse", "transfer", "coarse_solve", "factor",
+                      "krylov", "setup", "grads", "layout"]
 
 
 class PdeopError(RuntimeError):
@@ -74,7 +77,25 @@ class PdeopLibrary:
         d.pdeop_mg_setup.argtypes = [c_void_p, c_void_p] + [PP] * 3 + [c_void_p] * 4
         d.pdeop_stage.argtypes = [c_void_p, CFG, c_int, c_int, c_int] + [c_void_p] * 6
         d.pdeop_fgmres.argtypes = [c_void_p, CFG, c_int] + [c_void_p] * 7
+        d.pdeop_profile_enable.argtypes = [c_int]
+        d.pdeop_profile_enable.restype = None
+        d.pdeop_profile_collect.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong), c_int]
+        d.pdeop_launch_count.restype = ctypes.c_longlong
         self.backend = d.pdeop_backend_name().decode()
+
+    def profile_enable(self, on=True):
+        self.dll.pdeop_profile_enable(1 if on else 0)
+
+    def profile_collect(self):
+        """{category: (total_ms, launches_groups)} since profile_enable; waits for the recorded events."""
+        n = len(PROFILE_CATEGORIES)
+        ms = (ctypes.c_double * n)()
+        cnt = (ctypes.c_longlong * n)()
+        self.dll.pdeop_profile_collect(ms, cnt, n)
+        return {PROFILE_CATEGORIES[i]: (float(ms[i]), int(cnt[i])) for i in range(n)}
+
+    def launch_count(self):
+        return int(self.dll.pdeop_launch_count())
 
     def check(self, rc):
         if rc != 0:

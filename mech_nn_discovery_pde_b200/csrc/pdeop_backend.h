@@ -17,6 +17,12 @@ void be_free(void* p);
 void be_upload(void* dst, const void* src, size_t bytes);
 void be_zero(stream_t st, void* p, size_t bytes);
 int be_last_error(char* buf, int len);  // 0 if no pending error
+// timing events on the launching stream (cudaEvent_t in the CUDA build) and the launch counter
+void* be_event_create();
+void be_event_destroy(void* ev);
+void be_event_record(void* ev, stream_t st);
+float be_event_elapsed_ms(void* start, void* stop);  // waits for `stop`
+long long be_launch_count();
 
 void be_build_tables(stream_t st, const LevelDev& L, int B, const double* cv, const double* fv, const double* bv,
                      double* T);
@@ -35,10 +41,12 @@ void be_gs(stream_t st, const LevelDev& L, int B, const double* T, const double*
            int nsweeps, const int* done, int variant);
 void be_dense(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, double* Kd);
 // in-place lower Cholesky of B dense n x n matrices; state->chol_info set on a non-positive pivot
-void be_cholesky(stream_t st, int B, int n, double* Kd, FgmresState* state);
-// out = (L L^T)^-1 rhs
-void be_chol_solve(stream_t st, int B, int n, const double* Lf, const double* rhs, double* out, double* work,
-                   const int* done);
+// (bw = half-bandwidth of the matrix in the dense ordering; nothing outside the band is touched)
+void be_cholesky(stream_t st, int B, int n, int bw, double* Kd, FgmresState* state);
+// out = (L L^T)^-1 rhs for the dense system of level L (n = M*G); rhs/out in wave/planar layout, the
+// factor in band ordering; work: 2*B*n doubles
+void be_chol_solve(stream_t st, const LevelDev& L, int B, const double* Lf, const double* rhs, double* out,
+                   double* work, const int* done);
 void be_grads(stream_t st, const LevelDev& L, int B, const double* coef, const double* rhs_nat, const double* cv,
               const double* fv, const double* bv, const double* x, const double* dz, double* d_coeffs,
               double* d_rhs, double* d_iv, double* d_cv, double* d_fv, double* d_bv);

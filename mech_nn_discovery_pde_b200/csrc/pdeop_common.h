@@ -47,6 +47,11 @@ struct LevelDev {
     const int* rowbase;  // [(S+8)*N0] pos(i0,i1,i2) = rowbase[(s+4)*N0+i0] + i1
     const int* init_w;   // [n_init] wave index of each initial row's variable
     const int* init_m;   // [n_init] channel of each initial row's variable
+    // Dense (coarsest / dense-layer) ordering: unknown (w,m) -> band[w]*M + m, where band[] numbers the grid
+    // points with the LONGEST axis outermost, so that K is banded with half-bandwidth bw (stencil radius 4
+    // along the outer axis => bw = 4*inner*M + M - 1).  Cholesky creates no fill outside the band.
+    const int* band;     // [G]
+    int bw;
 };
 
 PDEOP_HD void unpack_coord(int c, int& i0, int& i1, int& i2) {

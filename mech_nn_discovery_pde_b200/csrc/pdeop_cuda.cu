@@ -25,7 +25,26 @@ static thread_local cudaError_t g_cuda_err = cudaSuccess;
 static inline void note(cudaError_t e) {
     if (e != cudaSuccess && g_cuda_err == cudaSuccess) g_cuda_err = e;
 }
+static long long g_launches = 0;   // kernels launched by this library (bench.py reports it)
 #define PDEOP_LAUNCH_CHECK() note(cudaGetLastError())
+#define PDEOP_COUNT(k) (g_launches += (k))
+long long be_launch_count() { return g_launches; }
+
+void* be_event_create() {
+    cudaEvent_t e = nullptr;
+    note(cudaEventCreate(&e));
+    return (void*)e;
+}
+void be_event_destroy(void* ev) {
+    if (ev) cudaEventDestroy((cudaEvent_t)ev);
+}
+void be_event_record(void* ev, stream_t st) { note(cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)st)); }
+float be_event_elapsed_ms(void* start, void* stop) {
+    float ms = 0.f;
+    note(cudaEventSynchronize((cudaEvent_t)stop));
+    note(cudaEventElapsedTime(&ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+    return ms;
+}
 
 const char* be_name() { return "cuda-sm100a"; }
 
@@ -75,6 +94,7 @@ void be_build_tables(stream_t st, const LevelDev& L, int B, const double* cv, co
                      double* T) {
     dim3 grid(cdiv(L.P, kThreads), L.D, B);
     k_build_tables<<<grid, kThreads, 0, (cudaStream_t)st>>>(L, cv, fv, bv, T);
+    PDEOP_COUNT(1);
     PDEOP_LAUNCH_CHECK();
 }
 
@@ -94,10 +114,12 @@ __global__ void __launch_bounds__(kThreads) k_unpack(LevelDev L, const double* _
 }
 void be_pack(stream_t st, const LevelDev& L, int B, const double* api, double* wave) {
     k_pack<<<dim3(cdiv(L.G, kThreads), B), kThreads, 0, (cudaStream_t)st>>>(L, api, wave);
+    PDEOP_COUNT(1);
     PDEOP_LAUNCH_CHECK();
 }
 void be_unpack(stream_t st, const LevelDev& L, int B, const double* wave, double* api) {
     k_unpack<<<dim3(cdiv(L.G, kThreads), B), kThreads, 0, (cudaStream_t)st>>>(L, wave, api);
+    PDEOP_COUNT(1);
     PDEOP_LAUNCH_CHECK();
 }
 
@@ -111,6 +133,7 @@ __global__ void __launch_bounds__(kThreads) k_interp(LevelDev Li, LevelDev Lo, i
 void be_interp(stream_t st, const LevelDev& Li, const LevelDev& Lo, int B, int C, const double* in, double* out,
                int add, const int* done) {
     k_interp<<<dim3(cdiv(Lo.G, kThreads), B), kThreads, 0, (cudaStream_t)st>>>(Li, Lo, C, in, out, add, done);
+    PDEOP_COUNT(1);
     PDEOP_LAUNCH_CHECK();
 }
 
@@ -129,6 +152,7 @@ __global__ void __launch_bounds__(kThreads) k_atb_init(LevelDev L, const double*
 void be_atb(stream_t st, const LevelDev& L, int B, const double* coef, const double* rhs_nat, const double* iv_rhs,
             double* atb) {
     k_atb<<<dim3(cdiv(L.G, kThreads), B), kThreads, 0, (cudaStream_t)st>>>(L, coef, rhs_nat, atb);
+    PDEOP_COUNT(1 + (L.n_init > 0));
     PDEOP_LAUNCH_CHECK();
     if (L.n_init > 0) {
         k_atb_init<<<dim3(cdiv(L.n_init, kThreads), B), kThreads, 0, (cudaStream_t)st>>>(L, iv_rhs, atb);
@@ -155,6 +179,7 @@ void be_apply_k(stream_t st, const LevelDev& L, int B, const double* T, const do
     if (L.D == 1) k_apply<1><<<grid, kThreads, 0, s>>>(L, T, coef, x, b, y, mode, done);
     else if (L.D == 2) k_apply<2><<<grid, kThreads, 0, s>>>(L, T, coef, x, b, y, mode, done);
     else k_apply<3><<<grid, kThreads, 0, s>>>(L, T, coef, x, b, y, mode, done);
+    PDEOP_COUNT(1);
     PDEOP_LAUNCH_CHECK();
 }
 
@@ -280,6 +305,7 @@ void be_gs(stream_t st, const LevelDev& L, int B, const double* T, const double*
         if (L.D == 1) launch_gs_cluster<1>(s, L, B, T, coef, b, x, nsweeps, done);
         else if (L.D == 2) launch_gs_cluster<2>(s, L, B, T, coef, b, x, nsweeps, done);
         else launch_gs_cluster<3>(s, L, B, T, coef, b, x, nsweeps, done);
+        PDEOP_COUNT(1);
         PDEOP_LAUNCH_CHECK();
         return;
     }
@@ -295,6 +321,7 @@ void be_gs(stream_t st, const LevelDev& L, int B, const double* T, const double*
         if (L.D == 1) k_gs_step<1><<<grid, kThreads, 0, s>>>(L, T, coef, b, x, nsweeps, t, done);
         else if (L.D == 2) k_gs_step<2><<<grid, kThreads, 0, s>>>(L, T, coef, b, x, nsweeps, t, done);
         else k_gs_step<3><<<grid, kThreads, 0, s>>>(L, T, coef, b, x, nsweeps, t, done);
+        PDEOP_COUNT(1);
     }
     PDEOP_LAUNCH_CHECK();
 }
@@ -317,6 +344,7 @@ void be_dense(stream_t st, const LevelDev& L, int B, const double* T, const doub
     if (L.D == 1) k_dense<1><<<grid, kThreads, 0, s>>>(L, T, coef, Kd);
     else if (L.D == 2) k_dense<2><<<grid, kThreads, 0, s>>>(L, T, coef, Kd);
     else k_dense<3><<<grid, kThreads, 0, s>>>(L, T, coef, Kd);
+    PDEOP_COUNT(1);
     PDEOP_LAUNCH_CHECK();
 }
 
@@ -349,6 +377,7 @@ void be_grads(stream_t st, const LevelDev& L, int B, const double* coef, const d
     if (L.D == 1) k_grads<1><<<grid, kThreads, 0, s>>>(L, coef, rhs_nat, cv, fv, bv, x, dz, d_coeffs, d_rhs, d_cv, d_fv, d_bv);
     else if (L.D == 2) k_grads<2><<<grid, kThreads, 0, s>>>(L, coef, rhs_nat, cv, fv, bv, x, dz, d_coeffs, d_rhs, d_cv, d_fv, d_bv);
     else k_grads<3><<<grid, kThreads, 0, s>>>(L, coef, rhs_nat, cv, fv, bv, x, dz, d_coeffs, d_rhs, d_cv, d_fv, d_bv);
+    PDEOP_COUNT(1 + (L.n_init > 0));
     PDEOP_LAUNCH_CHECK();
     if (L.n_init > 0) {
         k_grad_init<<<dim3(cdiv(L.n_init, kThreads), B), kThreads, 0, s>>>(L, dz, d_iv);
@@ -427,6 +456,7 @@ static void launch_dots(cudaStream_t s, size_t n, const double* V, size_t ldv, i
         else if (rem >= 4) { k_dots<4><<<nb, kThreads, 0, s>>>(n, V, ldv, k0, w, partial, done); k0 += 4; }
         else if (rem >= 2) { k_dots<2><<<nb, kThreads, 0, s>>>(n, V, ldv, k0, w, partial, done); k0 += 2; }
         else { k_dots<1><<<nb, kThreads, 0, s>>>(n, V, ldv, k0, w, partial, done); k0 += 1; }
+        PDEOP_COUNT(1);
     }
     PDEOP_LAUNCH_CHECK();
 }
@@ -449,6 +479,7 @@ void be_fg_begin(stream_t st, size_t n, const double* b, double* x, FgmresState*
     note(cudaMemsetAsync(x, 0, n * sizeof(double), cs));
     launch_dots(cs, n, b, 0, 1, b, state_partials(s, 0), nullptr);
     k_begin_final<<<1, 32, 0, cs>>>(s, reduce_blocks(n));
+    PDEOP_COUNT(1);
     PDEOP_LAUNCH_CHECK();
 }
 
@@ -466,6 +497,7 @@ void be_fg_resnorm(stream_t st, size_t n, const double* r, FgmresState* s, int m
     cudaStream_t cs = (cudaStream_t)st;
     launch_dots(cs, n, r, 0, 1, r, state_partials(s, 0), &s->done);
     k_resnorm_final<<<1, 32, 0, cs>>>(s, reduce_blocks(n), maxiter, atol);
+    PDEOP_COUNT(1);
     PDEOP_LAUNCH_CHECK();
 }
 
@@ -478,6 +510,7 @@ __global__ void __launch_bounds__(kThreads) k_first(size_t n, const double* __re
 }
 void be_fg_first(stream_t st, size_t n, const double* r, double* V0, FgmresState* s) {
     k_first<<<reduce_blocks(n), kThreads, 0, (cudaStream_t)st>>>(n, r, V0, s);
+    PDEOP_COUNT(1);
     PDEOP_LAUNCH_CHECK();
 }
 
@@ -534,6 +567,7 @@ void be_fg_cgs(stream_t st, size_t n, int j, int restart, double* V, double* w, 
     launch_dots(cs, n, V, n, j + 1, w, state_partials(s, 0), &s->done);
     k_axpy_norm<<<nb, kThreads, 0, cs>>>(n, j, restart, V, w, s, nb);
     k_scale_next<<<(j + 1 < restart) ? nb : 1, kThreads, 0, cs>>>(n, j, restart, V, w, s, nb);
+    PDEOP_COUNT(2);
     PDEOP_LAUNCH_CHECK();
 }
 
@@ -563,6 +597,7 @@ void be_fg_update(stream_t st, size_t n, int restart, const double* Z, double* x
     k_lstsq<<<1, 32, 0, cs>>>(s, restart);
     k_update<<<reduce_blocks(n), kThreads, 0, cs>>>(n, restart, Z, x, s);
     k_iters_add<<<1, 1, 0, cs>>>(s, restart);
+    PDEOP_COUNT(3);
     PDEOP_LAUNCH_CHECK();
 }
 
@@ -574,6 +609,7 @@ __global__ void k_info(const FgmresState* s, double* info4) {
 }
 void be_fg_info(stream_t st, const FgmresState* s, double* info4) {
     k_info<<<1, 1, 0, (cudaStream_t)st>>>(s, info4);
+    PDEOP_COUNT(1);
     PDEOP_LAUNCH_CHECK();
 }
 void be_fg_hess(stream_t st, const FgmresState* s, int restart, double* hess_out) {
@@ -627,7 +663,7 @@ __global__ void __launch_bounds__(256) k_chol_diag(int n, double* A, size_t stri
 }
 
 // rows r in [k0+nb, n):  A[r, k0:k0+nb] <- A[r, k0:k0+nb] * L11^-T
-__global__ void __launch_bounds__(128) k_chol_trsm(int n, double* A, size_t strideA, int k0, int nb) {
+__global__ void __launch_bounds__(128) k_chol_trsm(int n, double* A, size_t strideA, int k0, int nb, int r1) {
     __shared__ double l[kInner][kInner + 1];
     double* Ab = A + (size_t)blockIdx.y * strideA;
     for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) {
@@ -636,7 +672,7 @@ __global__ void __launch_bounds__(128) k_chol_trsm(int n, double* A, size_t stri
     }
     __syncthreads();
     const int r = k0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
+    if (r >= r1) return;
     double* row = Ab + (size_t)r * n + k0;
     double v[kInner];
 #pragma unroll
@@ -655,8 +691,8 @@ __global__ void __launch_bounds__(128) k_chol_trsm(int n, double* A, size_t stri
         if (j < nb) row[j] = v[j];
 }
 
-// C[i][j] -= sum_{t in [p0,p1)} A[i][t] A[j][t]   for i in [r0,n), j in [c0,c1), i >= j
-__global__ void __launch_bounds__(256) k_syrk(int n, double* A, size_t strideA, int r0, int c0, int c1, int p0,
+// C[i][j] -= sum_{t in [p0,p1)} A[i][t] A[j][t]   for i in [r0,r1), j in [c0,c1), i >= j
+__global__ void __launch_bounds__(256) k_syrk(int n, double* A, size_t strideA, int r0, int r1, int c0, int c1, int p0,
                                               int p1) {
     const int i0 = r0 + blockIdx.x * 64, j0 = c0 + blockIdx.y * 64;
     if (i0 + 63 < j0) return;
@@ -675,7 +711,7 @@ __global__ void __launch_bounds__(256) k_syrk(int n, double* A, size_t strideA, 
         for (int q = 0; q < 4; ++q) {
             const int k = kk + lk + q;
             const int ia = i0 + lrow, jb = j0 + lrow;
-            As[lk + q][lrow] = (ia < n && k < p1) ? Ab[(size_t)ia * n + k] : 0.0;
+            As[lk + q][lrow] = (ia < r1 && k < p1) ? Ab[(size_t)ia * n + k] : 0.0;
             Bs[lk + q][lrow] = (jb < c1 && k < p1) ? Ab[(size_t)jb * n + k] : 0.0;
         }
         __syncthreads();
@@ -698,17 +734,19 @@ __global__ void __launch_bounds__(256) k_syrk(int n, double* A, size_t strideA, 
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const int i = i0 + ty * 4 + a, j = j0 + tx * 4 + b;
-            if (i < n && j < c1 && i >= j) Ab[(size_t)i * n + j] -= acc[a][b];
+            if (i < r1 && j < c1 && i >= j) Ab[(size_t)i * n + j] -= acc[a][b];
         }
 }
 
-static void launch_syrk(cudaStream_t s, int B, int n, double* A, int r0, int c0, int c1, int p0, int p1) {
-    if (r0 >= n || c0 >= c1 || p0 >= p1) return;
-    dim3 grid(cdiv(n - r0, 64), cdiv(c1 - c0, 64), B);
-    k_syrk<<<grid, 256, 0, s>>>(n, A, (size_t)n * n, r0, c0, c1, p0, p1);
+static void launch_syrk(cudaStream_t s, int B, int n, double* A, int r0, int r1, int c0, int c1, int p0, int p1) {
+    if (r0 >= r1 || c0 >= c1 || p0 >= p1) return;
+    dim3 grid(cdiv(r1 - r0, 64), cdiv(c1 - c0, 64), B);
+    k_syrk<<<grid, 256, 0, s>>>(n, A, (size_t)n * n, r0, r1, c0, c1, p0, p1);
+    PDEOP_COUNT(1);
 }
 
-void be_cholesky(stream_t st, int B, int n, double* Kd, FgmresState* state) {
+// Band-limited: column k of L is nonzero only in rows [k, k+bw], so every update stops bw rows below its panel.
+void be_cholesky(stream_t st, int B, int n, int bw, double* Kd, FgmresState* state) {
     cudaStream_t s = (cudaStream_t)st;
     const size_t strideA = (size_t)n * n;
     for (int K0 = 0; K0 < n; K0 += kOuter) {
@@ -716,14 +754,20 @@ void be_cholesky(stream_t st, int B, int n, double* Kd, FgmresState* state) {
         for (int k0 = K0; k0 < K1; k0 += kInner) {
             const int nb = k0 + kInner < K1 ? kInner : K1 - k0;
             k_chol_diag<<<B, 256, 0, s>>>(n, Kd, strideA, k0, nb, state);
-            if (k0 + nb < n) {
-                k_chol_trsm<<<dim3(cdiv(n - k0 - nb, 128), B), 128, 0, s>>>(n, Kd, strideA, k0, nb);
+            PDEOP_COUNT(1);
+            const long long lim = (long long)k0 + nb + bw;
+            const int r1 = lim < n ? (int)lim : n;
+            if (k0 + nb < r1) {
+                k_chol_trsm<<<dim3(cdiv(r1 - k0 - nb, 128), B), 128, 0, s>>>(n, Kd, strideA, k0, nb, r1);
+                PDEOP_COUNT(1);
                 // rest of the outer panel: columns [k0+nb, K1)
-                launch_syrk(s, B, n, Kd, k0 + nb, k0 + nb, K1, k0, k0 + nb);
+                launch_syrk(s, B, n, Kd, k0 + nb, r1, k0 + nb, K1 < r1 ? K1 : r1, k0, k0 + nb);
             }
         }
-        // trailing matrix: columns [K1, n), depth kOuter
-        launch_syrk(s, B, n, Kd, K1, K1, n, K0, K1);
+        // trailing matrix: columns [K1, K1+bw), depth kOuter
+        const long long lim = (long long)K1 + bw;
+        const int r1 = lim < n ? (int)lim : n;
+        launch_syrk(s, B, n, Kd, K1, r1, K1, r1, K0, K1);
     }
     PDEOP_LAUNCH_CHECK();
 }
@@ -737,8 +781,8 @@ constexpr int kSolveSub = 64;
 
 // t[i] = r[i] - sum_{c<k0} L[i][c] y[c]   for rows i in [k0, k0+w): one warp per row
 __global__ void __launch_bounds__(256) k_fwd_gemv(int n, const double* __restrict__ Lf, size_t strideL, int k0, int w,
-                                                  const double* __restrict__ r, const double* __restrict__ y,
-                                                  double* __restrict__ t, const int* done) {
+                                                  int c_lo, const double* __restrict__ r, const double* y,
+                                                  double* t, const int* done) {
     if (done && *done) return;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= w) return;
@@ -747,7 +791,7 @@ __global__ void __launch_bounds__(256) k_fwd_gemv(int n, const double* __restric
     const double* Lr = Lf + (size_t)ib * strideL + (size_t)(k0 + row) * n;
     const double* yb = y + (size_t)ib * n;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int c = lane;
+    int c = c_lo + lane;
     for (; c + 96 < k0; c += 128) {
         a0 += Lr[c] * yb[c];
         a1 += Lr[c + 32] * yb[c + 32];
@@ -761,8 +805,7 @@ __global__ void __launch_bounds__(256) k_fwd_gemv(int n, const double* __restric
 
 // solve L_kk y_k = t_k in place (t -> y) for the block [k0, k0+w): one CTA per instance
 __global__ void __launch_bounds__(256) k_fwd_diag(int n, const double* __restrict__ Lf, size_t strideL, int k0, int w,
-                                                  const double* __restrict__ t, double* __restrict__ y,
-                                                  const int* done) {
+                                                  const double* t, double* y, const int* done) {
     if (done && *done) return;
     __shared__ double Ls[kSolveSub][kSolveSub + 1];
     __shared__ double ys[kSolveBlk];
@@ -835,16 +878,16 @@ __global__ void __launch_bounds__(256) k_bwd_diag(int n, const double* __restric
     for (int i = tid; i < w; i += blockDim.x) y[(size_t)ib * n + k0 + i] = zs[i];
 }
 
-// y[c] -= sum_{r in [k0,k0+w)} L[r][c] z[r]  for c < k0: one thread per column (coalesced along rows of L)
+// y[c] -= sum_{r in [k0,k0+w)} L[r][c] z[r]  for c in [c_lo,k0): one thread per column (coalesced along rows of L)
 __global__ void __launch_bounds__(256) k_bwd_update(int n, const double* __restrict__ Lf, size_t strideL, int k0,
-                                                    int w, double* __restrict__ y, const int* done) {
+                                                    int w, int c_lo, double* __restrict__ y, const int* done) {
     if (done && *done) return;
     __shared__ double zs[kSolveBlk];
     const int ib = blockIdx.y;
     double* yb = y + (size_t)ib * n;
     for (int i = threadIdx.x; i < w; i += blockDim.x) zs[i] = yb[k0 + i];
     __syncthreads();
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = c_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= k0) return;
     const double* Lc = Lf + (size_t)ib * strideL + (size_t)k0 * n + c;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -859,28 +902,65 @@ __global__ void __launch_bounds__(256) k_bwd_update(int n, const double* __restr
     yb[c] -= (a0 + a1) + (a2 + a3);
 }
 
-void be_chol_solve(stream_t st, int B, int n, const double* Lf, const double* rhs, double* out, double* work,
-                   const int* done) {
+__global__ void __launch_bounds__(kThreads) k_to_band(LevelDev L, const double* __restrict__ wave,
+                                                      double* __restrict__ bandv, const int* done) {
+    if (done && *done) return;
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= L.G) return;
+    const size_t o = (size_t)blockIdx.y * L.M * L.G;
+    to_band_elem(L, wave + o, bandv + o, w);
+}
+__global__ void __launch_bounds__(kThreads) k_from_band(LevelDev L, const double* __restrict__ bandv,
+                                                        double* __restrict__ wave, const int* done) {
+    if (done && *done) return;
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= L.G) return;
+    const size_t o = (size_t)blockIdx.y * L.M * L.G;
+    from_band_elem(L, bandv + o, wave + o, w);
+}
+
+void be_chol_solve(stream_t st, const LevelDev& L, int B, const double* Lf, const double* rhs, double* out,
+                   double* work, const int* done) {
     cudaStream_t s = (cudaStream_t)st;
+    const int n = L.M * L.G;
+    const int bw = L.bw;
     const size_t strideL = (size_t)n * n;
-    // forward: y (in `out`) = L^-1 rhs
+    double* rb = work;                  // right-hand side in band ordering
+    double* y = work + (size_t)B * n;   // solution in band ordering, solved in place
+    k_to_band<<<dim3(cdiv(L.G, kThreads), B), kThreads, 0, s>>>(L, rhs, rb, done);
+    PDEOP_COUNT(1);
+    // forward: y = L^-1 rb
     for (int k0 = 0; k0 < n; k0 += kSolveBlk) {
         const int w = k0 + kSolveBlk < n ? kSolveBlk : n - k0;
-        const double* tsrc = rhs;
+        const double* tsrc = rb;
         if (k0 > 0) {
-            k_fwd_gemv<<<dim3(cdiv(w, 8), B), 256, 0, s>>>(n, Lf, strideL, k0, w, rhs, out, work, done);
-            tsrc = work;
+            int c_lo = k0 - bw;
+            if (c_lo < 0) c_lo = 0;
+            c_lo &= ~31;
+            k_fwd_gemv<<<dim3(cdiv(w, 8), B), 256, 0, s>>>(n, Lf, strideL, k0, w, c_lo, rb, y, y, done);
+            PDEOP_COUNT(1);
+            tsrc = y;
         }
-        k_fwd_diag<<<B, 256, 0, s>>>(n, Lf, strideL, k0, w, tsrc, out, done);
+        k_fwd_diag<<<B, 256, 0, s>>>(n, Lf, strideL, k0, w, tsrc, y, done);
+        PDEOP_COUNT(1);
     }
-    // backward: out = L^-T y, in place
+    // backward: y = L^-T y, in place
     const int nblk = (n + kSolveBlk - 1) / kSolveBlk;
     for (int kb = nblk - 1; kb >= 0; --kb) {
         const int k0 = kb * kSolveBlk;
         const int w = k0 + kSolveBlk < n ? kSolveBlk : n - k0;
-        k_bwd_diag<<<B, 256, 0, s>>>(n, Lf, strideL, k0, w, out, done);
-        if (k0 > 0) k_bwd_update<<<dim3(cdiv(k0, 256), B), 256, 0, s>>>(n, Lf, strideL, k0, w, out, done);
+        k_bwd_diag<<<B, 256, 0, s>>>(n, Lf, strideL, k0, w, y, done);
+        PDEOP_COUNT(1);
+        if (k0 > 0) {
+            int c_lo = k0 - bw;
+            if (c_lo < 0) c_lo = 0;
+            c_lo &= ~31;
+            k_bwd_update<<<dim3(cdiv(k0 - c_lo, 256), B), 256, 0, s>>>(n, Lf, strideL, k0, w, c_lo, y, done);
+            PDEOP_COUNT(1);
+        }
     }
+    k_from_band<<<dim3(cdiv(L.G, kThreads), B), kThreads, 0, s>>>(L, y, out, done);
+    PDEOP_COUNT(1);
     PDEOP_LAUNCH_CHECK();
 }
 

@@ -371,7 +371,8 @@ PDEOP_HD void atb_init_elem(const LevelDev& L, const double* __restrict__ iv_rhs
 }
 
 // ------------------------------------------------------------------------------------------------
-// Dense K for one point: writes the M rows (m*G+w) of the pre-zeroed n x n matrix (n = M*G).
+// Dense K for one point: writes the M rows of the point into the pre-zeroed n x n matrix (n = M*G) in BAND
+// ordering: unknown (w,m) -> band[w]*M + m.
 // ------------------------------------------------------------------------------------------------
 template <int D>
 PDEOP_HD void dense_elem(const LevelDev& L, const double* __restrict__ T, const double* __restrict__ coef,
@@ -386,16 +387,17 @@ PDEOP_HD void dense_elem(const LevelDev& L, const double* __restrict__ T, const 
     const int idx[3] = {i0, i1, i2};
     PointLocal<D> pl;
     load_local<D>(L, T, coef, w, i0, i1, i2, flags, pl);
+    const size_t r0 = (size_t)L.band[w] * M;   // first row/col of this point
     // local block
     for (int m = 0; m < M; ++m)
         for (int k = 0; k < M; ++k) {
             double v = pl.c[m] * pl.c[k];
             if (m == k) v += pl.ini[m];
-            Kd[((size_t)m * G + w) * n + (size_t)k * G + w] = v;
+            Kd[(r0 + m) * n + r0 + k] = v;
         }
-    Kd[(size_t)w * n + w] += pl.uu;
+    Kd[r0 * n + r0] += pl.uu;
     for (int a = 0; a < D; ++a) {
-        const size_t ru = w, rp = (size_t)(1 + a) * G + w, rq = (size_t)(1 + D + a) * G + w;
+        const size_t ru = r0, rp = r0 + 1 + a, rq = r0 + 1 + D + a;
         Kd[ru * n + rp] += pl.up[a];
         Kd[rp * n + ru] += pl.up[a];
         Kd[ru * n + rq] += pl.uq[a];
@@ -411,7 +413,7 @@ PDEOP_HD void dense_elem(const LevelDev& L, const double* __restrict__ T, const 
         const int nn = L.N[ax];
         const int i = idx[ax];
         const double* Ta = T + (size_t)a * kTabEntries * P + (i + kTabPad);
-        const size_t ru = w, rp = (size_t)(1 + a) * G + w, rq = (size_t)(1 + D + a) * G + w;
+        const size_t ru = r0, rp = r0 + 1 + a, rq = r0 + 1 + D + a;
         for (int o = -4; o <= 4; ++o) {
             if (o == 0) continue;
             const int ii = i + o;
@@ -420,13 +422,24 @@ PDEOP_HD void dense_elem(const LevelDev& L, const double* __restrict__ T, const 
             if (ax == 2) wn = neighbor_pos<2>(L, s, i0, i1, o);
             else if (ax == 1) wn = neighbor_pos<1>(L, s, i0, i1, o);
             else wn = neighbor_pos<0>(L, s, i0, i1, o);
-            Kd[ru * n + wn] = Ta[(T_UU + o + 4) * P];
-            Kd[ru * n + (size_t)(1 + a) * G + wn] = Ta[(T_UP - o + 4) * P + o];
-            Kd[ru * n + (size_t)(1 + D + a) * G + wn] = Ta[(T_UQ - o + 4) * P + o];
-            Kd[rp * n + wn] = Ta[(T_UP + o + 4) * P];
-            Kd[rq * n + wn] = Ta[(T_UQ + o + 4) * P];
+            const size_t c0 = (size_t)L.band[wn] * M;
+            Kd[ru * n + c0] = Ta[(T_UU + o + 4) * P];
+            Kd[ru * n + c0 + 1 + a] = Ta[(T_UP - o + 4) * P + o];
+            Kd[ru * n + c0 + 1 + D + a] = Ta[(T_UQ - o + 4) * P + o];
+            Kd[rp * n + c0] = Ta[(T_UP + o + 4) * P];
+            Kd[rq * n + c0] = Ta[(T_UQ + o + 4) * P];
         }
     }
+}
+
+// wave/planar vector [m][w] <-> band-ordered vector [band[w]*M + m]
+PDEOP_HD void to_band_elem(const LevelDev& L, const double* __restrict__ wave, double* __restrict__ bandv, int w) {
+    const size_t r0 = (size_t)L.band[w] * L.M;
+    for (int m = 0; m < L.M; ++m) bandv[r0 + m] = wave[(size_t)m * L.G + w];
+}
+PDEOP_HD void from_band_elem(const LevelDev& L, const double* __restrict__ bandv, double* __restrict__ wave, int w) {
+    const size_t r0 = (size_t)L.band[w] * L.M;
+    for (int m = 0; m < L.M; ++m) wave[(size_t)m * L.G + w] = bandv[r0 + m];
 }
 
 // ------------------------------------------------------------------------------------------------

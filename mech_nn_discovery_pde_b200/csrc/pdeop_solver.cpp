@@ -22,6 +22,45 @@ using namespace pdeop;
 
 static thread_local std::string g_err;
 
+// ---- optional per-category timing with events on the launching stream (bench.py roofline numbers) ----
+enum ProfCat {
+    PC_GS_FINE = 0, PC_GS_COARSE, PC_APPLY_FINE, PC_APPLY_COARSE, PC_TRANSFER, PC_COARSE_SOLVE, PC_FACTOR,
+    PC_KRYLOV, PC_SETUP, PC_GRADS, PC_LAYOUT, PC_COUNT
+};
+struct ProfRec { int cat; void* a; void* b; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<void*> g_prof_pool;
+static void* prof_event() {
+    if (!g_prof_pool.empty()) { void* e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    return be_event_create();
+}
+struct ProfScope {
+    int cat; void* a = nullptr; stream_t st;
+    ProfScope(int c, stream_t s) : cat(c), st(s) {
+        if (g_prof_on) { a = prof_event(); be_event_record(a, st); }
+    }
+    ~ProfScope() {
+        if (a) { void* b = prof_event(); be_event_record(b, st); g_prof_recs.push_back({cat, a, b}); }
+    }
+};
+extern "C" void pdeop_profile_enable(int on) {
+    g_prof_on = on != 0;
+    for (auto& r : g_prof_recs) { g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b); }
+    g_prof_recs.clear();
+}
+extern "C" int pdeop_profile_collect(double* ms, long long* counts, int ncat) {
+    for (int i = 0; i < ncat; ++i) { ms[i] = 0.0; counts[i] = 0; }
+    for (auto& r : g_prof_recs) {
+        if (r.cat < ncat) { ms[r.cat] += be_event_elapsed_ms(r.a, r.b); counts[r.cat] += 1; }
+        g_prof_pool.push_back(r.a);
+        g_prof_pool.push_back(r.b);
+    }
+    g_prof_recs.clear();
+    return PC_COUNT;
+}
+extern "C" long long pdeop_launch_count(void) { return be_launch_count(); }
+
 static int fail(const std::string& msg) {
     g_err = msg;
     return 1;
@@ -132,6 +171,23 @@ static int build_level(pdeop_plan* pl, LevelHost& lh, const int* dims, int n_iv,
                 }
     }
     L.n_init = (int)init_w.size();
+    // band ordering for the dense path: longest axis outermost
+    {
+        int outer = 0;
+        for (int a = 1; a < 3; ++a)
+            if (L.N[a] > L.N[outer]) outer = a;
+        const int in1 = outer == 0 ? 1 : 0, in2 = outer == 2 ? 1 : 2;
+        const int inner = L.N[in1] * L.N[in2];
+        std::vector<int> band(L.G);
+        for (int ww = 0; ww < L.G; ++ww) {
+            int idx[3];
+            unpack_coord(coord[ww], idx[0], idx[1], idx[2]);
+            band[ww] = idx[outer] * inner + idx[in1] * L.N[in2] + idx[in2];
+        }
+        L.band = upload_vec(lh, band);
+        L.bw = 4 * inner * L.M + L.M - 1;
+        if (L.bw > L.M * L.G - 1) L.bw = L.M * L.G - 1;
+    }
     L.coord = upload_vec(lh, coord);
     L.flags = upload_vec(lh, flags);
     L.hstart = upload_vec(lh, hstart);
@@ -278,18 +334,23 @@ static void setup_operator(pdeop_plan* pl, const double* coeffs, const double* c
                            const double* const* bv, void* persist, Scratch& sc, stream_t st) {
     const int B = pl->B;
     be_state_reset(st, sc.state);
-    be_pack(st, pl->lev[0].dev, B, coeffs, P_coef(pl, persist, 0));
-    for (int l = 0; l < pl->n_grid; ++l) {
-        const LevelDev& L = pl->lev[l].dev;
-        if (l > 0)
-            be_interp(st, pl->lev[l - 1].dev, L, B, L.M, P_coef(pl, persist, l - 1), P_coef(pl, persist, l), 0, nullptr);
-        be_build_tables(st, L, B, cv[l], fv[l], bv[l], P_T(pl, persist, l));
+    {
+        ProfScope ps(PC_SETUP, st);
+        be_pack(st, pl->lev[0].dev, B, coeffs, P_coef(pl, persist, 0));
+        for (int l = 0; l < pl->n_grid; ++l) {
+            const LevelDev& L = pl->lev[l].dev;
+            if (l > 0)
+                be_interp(st, pl->lev[l - 1].dev, L, B, L.M, P_coef(pl, persist, l - 1), P_coef(pl, persist, l), 0,
+                          nullptr);
+            be_build_tables(st, L, B, cv[l], fv[l], bv[l], P_T(pl, persist, l));
+        }
+        const int lc = pl->n_grid - 1;
+        double* Kd = P_Kd(pl, persist);
+        be_zero(st, Kd, (size_t)B * pl->nc * pl->nc * sizeof(double));
+        be_dense(st, pl->lev[lc].dev, B, P_T(pl, persist, lc), P_coef(pl, persist, lc), Kd);
     }
-    const int lc = pl->n_grid - 1;
-    double* Kd = P_Kd(pl, persist);
-    be_zero(st, Kd, (size_t)B * pl->nc * pl->nc * sizeof(double));
-    be_dense(st, pl->lev[lc].dev, B, P_T(pl, persist, lc), P_coef(pl, persist, lc), Kd);
-    be_cholesky(st, B, pl->nc, Kd, sc.state);
+    ProfScope pf(PC_FACTOR, st);
+    be_cholesky(st, B, pl->nc, pl->lev[pl->n_grid - 1].dev.bw, P_Kd(pl, persist), sc.state);
 }
 
 static void vcycle(pdeop_plan* pl, const pdeop_solver_cfg* cfg, void* persist, Scratch& sc, int l, const double* b,
@@ -297,17 +358,31 @@ static void vcycle(pdeop_plan* pl, const pdeop_solver_cfg* cfg, void* persist, S
     const int B = pl->B;
     const LevelDev& L = pl->lev[l].dev;
     const int* done = &sc.state->done;
-    be_gs(st, L, B, P_T(pl, persist, l), P_coef(pl, persist, l), b, x, cfg->gs_pre, done, cfg->gs_variant);
-    be_apply_k(st, L, B, P_T(pl, persist, l), P_coef(pl, persist, l), x, b, rtmp, 1, done);
+    {
+        ProfScope ps(l == 0 ? PC_GS_FINE : PC_GS_COARSE, st);
+        be_gs(st, L, B, P_T(pl, persist, l), P_coef(pl, persist, l), b, x, cfg->gs_pre, done, cfg->gs_variant);
+    }
+    {
+        ProfScope ps(l == 0 ? PC_APPLY_FINE : PC_APPLY_COARSE, st);
+        be_apply_k(st, L, B, P_T(pl, persist, l), P_coef(pl, persist, l), x, b, rtmp, 1, done);
+    }
     const LevelDev& Lc = pl->lev[l + 1].dev;
-    be_interp(st, L, Lc, B, L.M, rtmp, sc.lb[l + 1], 0, done);
+    {
+        ProfScope ps(PC_TRANSFER, st);
+        be_interp(st, L, Lc, B, L.M, rtmp, sc.lb[l + 1], 0, done);
+    }
     if (l + 1 == pl->n_grid - 1) {
-        be_chol_solve(st, B, pl->nc, P_Kd(pl, persist), sc.lb[l + 1], sc.lx[l + 1], sc.cwork, done);
+        ProfScope ps(PC_COARSE_SOLVE, st);
+        be_chol_solve(st, Lc, B, P_Kd(pl, persist), sc.lb[l + 1], sc.lx[l + 1], sc.cwork, done);
     } else {
         be_zero(st, sc.lx[l + 1], (size_t)B * Lc.M * Lc.G * sizeof(double));
         vcycle(pl, cfg, persist, sc, l + 1, sc.lb[l + 1], sc.lx[l + 1], sc.lr[l + 1], st);
     }
-    be_interp(st, Lc, L, B, L.M, sc.lx[l + 1], x, 1, done);
+    {
+        ProfScope ps(PC_TRANSFER, st);
+        be_interp(st, Lc, L, B, L.M, sc.lx[l + 1], x, 1, done);
+    }
+    ProfScope ps(l == 0 ? PC_GS_FINE : PC_GS_COARSE, st);
     be_gs(st, L, B, P_T(pl, persist, l), P_coef(pl, persist, l), b, x, cfg->gs_post, done, cfg->gs_variant);
 }
 
@@ -328,19 +403,33 @@ static void fgmres(pdeop_plan* pl, const pdeop_solver_cfg* cfg, void* persist, S
     const double* c0 = P_coef(pl, persist, 0);
     const int m = cfg->restart;
     const int* done = &sc.state->done;
-    be_fg_begin(st, sc.n0, b, x, sc.state);
+    {
+        ProfScope ps(PC_KRYLOV, st);
+        be_fg_begin(st, sc.n0, b, x, sc.state);
+    }
     const int ncycles = (cfg->max_iter + m - 1) / m;
     for (int cyc = 0;; ++cyc) {
-        be_apply_k(st, L0, B, T0, c0, x, b, sc.w, 1, done);
-        be_fg_resnorm(st, sc.n0, sc.w, sc.state, cfg->max_iter, cfg->atol);
-        if (cyc == ncycles) break;
-        be_fg_first(st, sc.n0, sc.w, sc.V, sc.state);
+        {
+            ProfScope ps(PC_APPLY_FINE, st);
+            be_apply_k(st, L0, B, T0, c0, x, b, sc.w, 1, done);
+        }
+        {
+            ProfScope ps(PC_KRYLOV, st);
+            be_fg_resnorm(st, sc.n0, sc.w, sc.state, cfg->max_iter, cfg->atol);
+            if (cyc == ncycles) break;
+            be_fg_first(st, sc.n0, sc.w, sc.V, sc.state);
+        }
         for (int j = 0; j < m; ++j) {
             double* zj = sc.Z + (size_t)j * sc.n0;
             vcycle_start(pl, cfg, persist, sc, sc.V + (size_t)j * sc.n0, zj, sc.w, st);
-            be_apply_k(st, L0, B, T0, c0, zj, nullptr, sc.w, 0, done);
+            {
+                ProfScope ps(PC_APPLY_FINE, st);
+                be_apply_k(st, L0, B, T0, c0, zj, nullptr, sc.w, 0, done);
+            }
+            ProfScope ps(PC_KRYLOV, st);
             be_fg_cgs(st, sc.n0, j, m, sc.V, sc.w, sc.state);
         }
+        ProfScope ps(PC_KRYLOV, st);
         be_fg_update(st, sc.n0, m, sc.Z, x, sc.state);
     }
 }
@@ -384,6 +473,7 @@ static void run_grads(pdeop_plan* pl, void* persist, Scratch& sc, const double* 
     const LevelDev& L0 = pl->lev[0].dev;
     const int B = pl->B;
     double* xw = sc.V;  // Krylov basis no longer needed
+    ProfScope ps(PC_GRADS, st);
     be_pack(st, L0, B, x_api, xw);
     be_zero(st, d_cv, (size_t)B * L0.Ntot * 12 * sizeof(double));
     be_zero(st, d_fv, (size_t)B * L0.Ftot * 4 * sizeof(double));
@@ -419,7 +509,7 @@ extern "C" int pdeop_dense_forward(pdeop_plan* pl, const double* coeffs, const d
     const double* bvp[1] = {bv0};
     setup_operator(pl, coeffs, cvp, fvp, bvp, persist, sc, stream);
     be_atb(stream, pl->lev[0].dev, pl->B, P_coef(pl, persist, 0), rhs, iv_rhs, sc.atb);
-    be_chol_solve(stream, pl->B, pl->nc, P_Kd(pl, persist), sc.atb, sc.x, sc.cwork, nullptr);
+    be_chol_solve(stream, pl->lev[0].dev, pl->B, P_Kd(pl, persist), sc.atb, sc.x, sc.cwork, nullptr);
     be_unpack(stream, pl->lev[0].dev, pl->B, sc.x, x_out);
     if (info_out) be_fg_info(stream, sc.state, info_out);
     return check_backend();
@@ -434,7 +524,7 @@ extern "C" int pdeop_dense_backward(pdeop_plan* pl, const double* rhs, const dou
     Scratch sc = carve(pl, scratch, 1);
     be_state_reset(stream, sc.state);
     be_pack(stream, pl->lev[0].dev, pl->B, grad_x, sc.atb);
-    be_chol_solve(stream, pl->B, pl->nc, P_Kd(pl, persist), sc.atb, sc.x, sc.cwork, nullptr);  // dz (:65)
+    be_chol_solve(stream, pl->lev[0].dev, pl->B, P_Kd(pl, persist), sc.atb, sc.x, sc.cwork, nullptr);  // dz (:65)
     if (info_out) be_fg_info(stream, sc.state, info_out);
     run_grads(pl, persist, sc, rhs, cv0, fv0, bv0, x, sc.x, d_coeffs, d_rhs, d_iv_rhs, d_cv, d_fv, d_bv, stream);
     return check_backend();
@@ -508,7 +598,7 @@ extern "C" int pdeop_stage(pdeop_plan* pl, const pdeop_solver_cfg* cfg, int stag
         case PDEOP_STAGE_COARSE_SOLVE:
             if (level != pl->n_grid - 1) return fail("coarse solve runs on the last level");
             be_pack(stream, L, B, in1, t1);
-            be_chol_solve(stream, B, pl->nc, P_Kd(pl, persist), t1, t2, sc.cwork, nullptr);
+            be_chol_solve(stream, L, B, P_Kd(pl, persist), t1, t2, sc.cwork, nullptr);
             be_unpack(stream, L, B, t2, out);
             break;
         case PDEOP_STAGE_ATB:

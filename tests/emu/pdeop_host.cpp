@@ -26,6 +26,11 @@ void be_free(void* p) { free(p); }
 void be_upload(void* dst, const void* src, size_t bytes) { if (bytes) memcpy(dst, src, bytes); }
 void be_zero(stream_t, void* p, size_t bytes) { memset(p, 0, bytes); }
 int be_last_error(char*, int) { return 0; }
+void* be_event_create() { return nullptr; }
+void be_event_destroy(void*) {}
+void be_event_record(void*, stream_t) {}
+float be_event_elapsed_ms(void*, void*) { return 0.f; }
+long long be_launch_count() { return 0; }
 
 static inline size_t vstride(const LevelDev& L) { return (size_t)L.M * L.G; }
 static inline size_t tstride(const LevelDev& L) { return (size_t)L.D * kTabEntries * L.P; }
@@ -119,7 +124,7 @@ void be_dense(stream_t, const LevelDev& L, int B, const double* T, const double*
         }
 }
 
-void be_cholesky(stream_t, int B, int n, double* Kd, FgmresState* state) {
+void be_cholesky(stream_t, int B, int n, int, double* Kd, FgmresState* state) {
     for (int ib = 0; ib < B; ++ib) {
         double* A = Kd + (size_t)ib * n * n;
         for (int j = 0; j < n; ++j) {
@@ -140,15 +145,16 @@ void be_cholesky(stream_t, int B, int n, double* Kd, FgmresState* state) {
     }
 }
 
-void be_chol_solve(stream_t, int B, int n, const double* Lf, const double* rhs, double* out, double*,
+void be_chol_solve(stream_t, const LevelDev& L, int B, const double* Lf, const double* rhs, double* out, double* work,
                    const int* done) {
     if (done && *done) return;
+    const int n = L.M * L.G;
     for (int ib = 0; ib < B; ++ib) {
         const double* A = Lf + (size_t)ib * n * n;
-        const double* r = rhs + (size_t)ib * n;
-        double* y = out + (size_t)ib * n;
+        double* y = work + (size_t)ib * n;
+        for (int w = 0; w < L.G; ++w) to_band_elem(L, rhs + (size_t)ib * n, y, w);
         for (int i = 0; i < n; ++i) {
-            double v = r[i];
+            double v = y[i];
             for (int k = 0; k < i; ++k) v -= A[(size_t)i * n + k] * y[k];
             y[i] = v / A[(size_t)i * n + i];
         }
@@ -157,6 +163,7 @@ void be_chol_solve(stream_t, int B, int n, const double* Lf, const double* rhs, 
             for (int k = i + 1; k < n; ++k) v -= A[(size_t)k * n + i] * y[k];
             y[i] = v / A[(size_t)i * n + i];
         }
+        for (int w = 0; w < L.G; ++w) from_band_elem(L, y, out + (size_t)ib * n, w);
     }
 }
 
