@@ -37,16 +37,19 @@ void be_apply_k(stream_t st, const LevelDev& L, int B, const double* T, const do
                 const double* b, double* y, int mode, const int* done);
 // nsweeps lexicographic Gauss-Seidel sweeps, in place.  variant 0: production kernel; 1: one launch per
 // hyperplane step (test cross-check).
-void be_gs(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, const double* b, double* x,
-           int nsweeps, const int* done, int variant);
+void be_gs(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, const double* dinv,
+           const double* b, double* x, int nsweeps, const int* done, int variant);
+// dinv[m][w] = 1 / K[(w,m),(w,m)]: reciprocal diagonal of K, computed once per operator set-up
+void be_dinv(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, double* dinv);
 void be_dense(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, double* Kd);
 // in-place lower Cholesky of B dense n x n matrices; state->chol_info set on a non-positive pivot
 // (bw = half-bandwidth of the matrix in the dense ordering; nothing outside the band is touched)
-void be_cholesky(stream_t st, int B, int n, int bw, double* Kd, FgmresState* state);
+// Linv: B * ceil(n/kSolveBlk) * kSolveBlk^2 doubles receiving the inverses of the diagonal blocks of L
+void be_cholesky(stream_t st, int B, int n, int bw, double* Kd, double* Linv, FgmresState* state);
 // out = (L L^T)^-1 rhs for the dense system of level L (n = M*G); rhs/out in wave/planar layout, the
 // factor in band ordering; work: 2*B*n doubles
-void be_chol_solve(stream_t st, const LevelDev& L, int B, const double* Lf, const double* rhs, double* out,
-                   double* work, const int* done);
+void be_chol_solve(stream_t st, const LevelDev& L, int B, const double* Lf, const double* Linv, const double* rhs,
+                   double* out, double* work, const int* done);
 void be_grads(stream_t st, const LevelDev& L, int B, const double* coef, const double* rhs_nat, const double* cv,
               const double* fv, const double* bv, const double* x, const double* dz, double* d_coeffs,
               double* d_rhs, double* d_iv, double* d_cv, double* d_fv, double* d_bv);

@@ -22,8 +22,12 @@ namespace pdeop {
 
 constexpr int kTabEntries = 30;   // Cuu[9] | Cup[9] | Cuq[9] | pp | qq | pq
 constexpr int kTabPad = 4;        // stencil radius of K along an axis
+// Fixed table pitch (max extent 1023 + 2*4 padding, rounded): a compile-time constant so that every table
+// load of a stencil kernel is [position pointer + immediate offset] with no address arithmetic.
+constexpr int kTabPitch = 1032;
 constexpr int kGsLag = 5;         // hyperplane lag between pipelined Gauss-Seidel sweeps (radius + 1)
 constexpr int kMaxRestart = 32;
+constexpr int kSolveBlk = 256;    // block size of the dense triangular solves (inverse diagonal blocks)
 
 enum TabIdx { T_UU = 0, T_UP = 9, T_UQ = 18, T_PP = 27, T_QQ = 28, T_PQ = 29 };
 
@@ -34,7 +38,7 @@ struct LevelDev {
     int M;           // channels = 1 + 2*D
     int G;           // grid points
     int S;           // hyperplanes = N0+N1+N2-2
-    int P;           // table pitch = max(N)+8
+    int P;           // table pitch (= kTabPitch)
     int n_init;      // initial/boundary rows
     int n_eq;        // equation rows
     int Ntot;        // sum of active extents          (central row-value table length)
@@ -44,7 +48,7 @@ struct LevelDev {
     const int* coord;    // [G]  i0 | i1<<10 | i2<<20, wave order
     const int* flags;    // [G]  bit0: carries an equation row; bits 4+2m..5+2m: # initial rows on channel m
     const int* hstart;   // [S+1] first wave index of each hyperplane
-    const int* rowbase;  // [(S+8)*N0] pos(i0,i1,i2) = rowbase[(s+4)*N0+i0] + i1
+    const int* rowbase;  // [(S+8)*N0] pos(i0,i1,i2) = rowbase[(s+4)*N0+i0] + i1  (4 spare ints either side)
     const int* init_w;   // [n_init] wave index of each initial row's variable
     const int* init_m;   // [n_init] channel of each initial row's variable
     // Dense (coarsest / dense-layer) ordering: unknown (w,m) -> band[w]*M + m, where band[] numbers the grid

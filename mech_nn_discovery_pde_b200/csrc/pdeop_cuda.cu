@@ -11,6 +11,7 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "pdeop_backend.h"
@@ -73,8 +74,6 @@ int be_last_error(char* buf, int len) {
 }
 
 constexpr int kThreads = 256;
-static inline size_t vstride(const LevelDev& L) { return (size_t)L.M * L.G; }
-static inline size_t tstride(const LevelDev& L) { return (size_t)L.D * kTabEntries * L.P; }
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
 // =================================================================================================
@@ -87,7 +86,7 @@ __global__ void __launch_bounds__(kThreads) k_build_tables(LevelDev L, const dou
     const int a = blockIdx.y, b = blockIdx.z;
     if (ip >= L.P) return;
     build_table_elem(L, a, ip, cv + (size_t)b * L.Ntot * 12, fv + (size_t)b * L.Ftot * 4, bv + (size_t)b * L.Ftot * 4,
-                     T + ((size_t)b * L.D + a) * kTabEntries * L.P);
+                     T + ((size_t)b * L.D + a) * kTabEntries * kTabPitch);
 }
 
 void be_build_tables(stream_t st, const LevelDev& L, int B, const double* cv, const double* fv, const double* bv,
@@ -169,7 +168,7 @@ __global__ void __launch_bounds__(kThreads) k_apply(LevelDev L, const double* __
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= L.G) return;
     const size_t o = (size_t)blockIdx.y * L.M * L.G;
-    apply_k_elem<D>(L, T + (size_t)blockIdx.y * L.D * kTabEntries * L.P, coef + o, x + o, b ? b + o : nullptr, y + o, w,
+    apply_k_elem<D>(L, T + (size_t)blockIdx.y * L.D * kTabEntries * kTabPitch, coef + o, x + o, b ? b + o : nullptr, y + o, w,
                     mode);
 }
 void be_apply_k(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, const double* x,
@@ -191,14 +190,14 @@ void be_apply_k(stream_t st, const LevelDev& L, int B, const double* T, const do
 // then the cluster barrier (release/acquire) orders the in-place iterate for the next step.
 // The iterate is read at the L2 coherence point (LdL2) because other CTAs of the cluster write it.
 // =================================================================================================
-constexpr int kGsThreads = 512;
 constexpr int kGsMaxSweeps = 16;
 
-template <int D>
-__global__ void __launch_bounds__(kGsThreads, 1) k_gs_cluster(LevelDev L, const double* __restrict__ T,
-                                                              const double* __restrict__ coef,
-                                                              const double* __restrict__ b, double* x, int nsweeps,
-                                                              const int* done) {
+template <int D, int THREADS, class LD>
+__global__ void __launch_bounds__(THREADS, 1) k_gs_cluster(LevelDev L, const double* __restrict__ T,
+                                                           const double* __restrict__ coef,
+                                                           const double* __restrict__ dinv,
+                                                           const double* __restrict__ b, double* x, int nsweeps,
+                                                           const int* done) {
     if (done && *done) return;
     cg::cluster_group cluster = cg::this_cluster();
     const int csize = (int)cluster.num_blocks();
@@ -207,7 +206,7 @@ __global__ void __launch_bounds__(kGsThreads, 1) k_gs_cluster(LevelDev L, const 
     const int tid = rank * blockDim.x + threadIdx.x;
     const int nthreads = csize * blockDim.x;
     const size_t o = (size_t)ib * L.M * L.G;
-    const double* Ti = T + (size_t)ib * L.D * kTabEntries * L.P;
+    const double* Ti = T + (size_t)ib * L.D * kTabEntries * kTabPitch;
     const int steps = L.S + kGsLag * (nsweeps - 1);
     for (int t = 0; t < steps; ++t) {
         // active hyperplanes of this step: s_k = t - lag*k for sweep k
@@ -231,8 +230,10 @@ __global__ void __launch_bounds__(kGsThreads, 1) k_gs_cluster(LevelDev L, const 
                 }
                 rem -= cnt;
             }
-            gs_elem<D, LdL2>(L, Ti, coef + o, b + o, x + o, w);
+            gs_elem<D, LD>(L, Ti, coef + o, dinv + o, b + o, x + o, w);
         }
+        // release/acquire at cluster scope; the acquire side invalidates L1 (CCTL.IVALL), so the next
+        // step's plain loads of x see what the other CTAs of the cluster wrote in this one
         cluster.sync();
     }
 }
@@ -240,7 +241,8 @@ __global__ void __launch_bounds__(kGsThreads, 1) k_gs_cluster(LevelDev L, const 
 // cross-check variant: one launch per step, no intra-kernel synchronisation
 template <int D>
 __global__ void __launch_bounds__(kThreads) k_gs_step(LevelDev L, const double* __restrict__ T,
-                                                      const double* __restrict__ coef, const double* __restrict__ b,
+                                                      const double* __restrict__ coef,
+                                                      const double* __restrict__ dinv, const double* __restrict__ b,
                                                       double* x, int nsweeps, int t, const int* done) {
     if (done && *done) return;
     const int k = blockIdx.z;
@@ -250,7 +252,8 @@ __global__ void __launch_bounds__(kThreads) k_gs_step(LevelDev L, const double* 
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= cnt) return;
     const size_t o = (size_t)blockIdx.y * L.M * L.G;
-    gs_elem<D, LdL2>(L, T + (size_t)blockIdx.y * L.D * kTabEntries * L.P, coef + o, b + o, x + o, h0 + j);
+    gs_elem<D, LdL2>(L, T + (size_t)blockIdx.y * L.D * kTabEntries * kTabPitch, coef + o, dinv + o, b + o, x + o,
+                     h0 + j);
 }
 
 static int g_num_sms = 0;
@@ -264,27 +267,37 @@ static int num_sms() {
     return g_num_sms;
 }
 
+// tuning switches (read once): PDEOP_GS_THREADS = 512 | 1024, PDEOP_GS_LD = l1 | l2
+static int g_gs_threads = 0, g_gs_l2 = -1;
+static void gs_tuning() {
+    if (g_gs_threads) return;
+    const char* e = getenv("PDEOP_GS_THREADS");
+    g_gs_threads = (e && atoi(e) == 1024) ? 1024 : 512;
+    const char* l = getenv("PDEOP_GS_LD");
+    g_gs_l2 = (l && strcmp(l, "l2") == 0) ? 1 : 0;
+}
+
 template <int D>
 static void launch_gs_cluster(cudaStream_t s, const LevelDev& L, int B, const double* T, const double* coef,
-                              const double* b, double* x, int nsweeps, const int* done) {
+                              const double* dinv, const double* b, double* x, int nsweeps, const int* done) {
+    gs_tuning();
+    const int threads = g_gs_threads;
     // cluster size: as many CTAs per instance as fit on the chip at once, capped by the portable
     // maximum (8) and by the work of one step (largest hyperplane x sweeps in flight)
     int maxh = 0;
     {
-        int n0 = L.N[0], n1 = L.N[1], n2 = L.N[2];
-        // largest hyperplane has at most min over axis pairs of the product of the two other extents
-        int a = n0 * n1, bb = n0 * n2, c = n1 * n2;
+        int a = L.N[0] * L.N[1], bb = L.N[0] * L.N[2], c = L.N[1] * L.N[2];
         maxh = a < bb ? a : bb;
         maxh = maxh < c ? maxh : c;
     }
-    int want = (maxh * (nsweeps < 5 ? nsweeps : 5) + kGsThreads - 1) / kGsThreads;
+    int want = (maxh * (nsweeps < 5 ? nsweeps : 5) + threads - 1) / threads;
     int fit = num_sms() / (B > 0 ? B : 1);
     int csize = 1;
     while (csize * 2 <= 8 && csize * 2 <= fit && csize < want) csize *= 2;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(B * csize));
-    cfg.blockDim = dim3(kGsThreads);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -294,17 +307,41 @@ static void launch_gs_cluster(cudaStream_t s, const LevelDev& L, int B, const do
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    note(cudaLaunchKernelEx(&cfg, k_gs_cluster<D>, L, T, coef, b, x, nsweeps, done));
+    if (threads == 1024) {
+        if (g_gs_l2) note(cudaLaunchKernelEx(&cfg, k_gs_cluster<D, 1024, LdL2>, L, T, coef, dinv, b, x, nsweeps, done));
+        else note(cudaLaunchKernelEx(&cfg, k_gs_cluster<D, 1024, LdPlain>, L, T, coef, dinv, b, x, nsweeps, done));
+    } else {
+        if (g_gs_l2) note(cudaLaunchKernelEx(&cfg, k_gs_cluster<D, 512, LdL2>, L, T, coef, dinv, b, x, nsweeps, done));
+        else note(cudaLaunchKernelEx(&cfg, k_gs_cluster<D, 512, LdPlain>, L, T, coef, dinv, b, x, nsweeps, done));
+    }
 }
 
-void be_gs(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, const double* b, double* x,
-           int nsweeps, const int* done, int variant) {
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_dinv(LevelDev L, const double* __restrict__ T,
+                                                   const double* __restrict__ coef, double* __restrict__ dinv) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= L.G) return;
+    const size_t o = (size_t)blockIdx.y * L.M * L.G;
+    dinv_elem<D>(L, T + (size_t)blockIdx.y * L.D * kTabEntries * kTabPitch, coef + o, dinv + o, w);
+}
+void be_dinv(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, double* dinv) {
+    dim3 grid(cdiv(L.G, kThreads), B);
+    cudaStream_t s = (cudaStream_t)st;
+    if (L.D == 1) k_dinv<1><<<grid, kThreads, 0, s>>>(L, T, coef, dinv);
+    else if (L.D == 2) k_dinv<2><<<grid, kThreads, 0, s>>>(L, T, coef, dinv);
+    else k_dinv<3><<<grid, kThreads, 0, s>>>(L, T, coef, dinv);
+    PDEOP_COUNT(1);
+    PDEOP_LAUNCH_CHECK();
+}
+
+void be_gs(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, const double* dinv,
+           const double* b, double* x, int nsweeps, const int* done, int variant) {
     if (nsweeps <= 0) return;
     cudaStream_t s = (cudaStream_t)st;
     if (variant == 0) {
-        if (L.D == 1) launch_gs_cluster<1>(s, L, B, T, coef, b, x, nsweeps, done);
-        else if (L.D == 2) launch_gs_cluster<2>(s, L, B, T, coef, b, x, nsweeps, done);
-        else launch_gs_cluster<3>(s, L, B, T, coef, b, x, nsweeps, done);
+        if (L.D == 1) launch_gs_cluster<1>(s, L, B, T, coef, dinv, b, x, nsweeps, done);
+        else if (L.D == 2) launch_gs_cluster<2>(s, L, B, T, coef, dinv, b, x, nsweeps, done);
+        else launch_gs_cluster<3>(s, L, B, T, coef, dinv, b, x, nsweeps, done);
         PDEOP_COUNT(1);
         PDEOP_LAUNCH_CHECK();
         return;
@@ -318,9 +355,9 @@ void be_gs(stream_t st, const LevelDev& L, int B, const double* T, const double*
     const int steps = L.S + kGsLag * (nsweeps - 1);
     dim3 grid(cdiv(maxh, kThreads), B, nsweeps);
     for (int t = 0; t < steps; ++t) {
-        if (L.D == 1) k_gs_step<1><<<grid, kThreads, 0, s>>>(L, T, coef, b, x, nsweeps, t, done);
-        else if (L.D == 2) k_gs_step<2><<<grid, kThreads, 0, s>>>(L, T, coef, b, x, nsweeps, t, done);
-        else k_gs_step<3><<<grid, kThreads, 0, s>>>(L, T, coef, b, x, nsweeps, t, done);
+        if (L.D == 1) k_gs_step<1><<<grid, kThreads, 0, s>>>(L, T, coef, dinv, b, x, nsweeps, t, done);
+        else if (L.D == 2) k_gs_step<2><<<grid, kThreads, 0, s>>>(L, T, coef, dinv, b, x, nsweeps, t, done);
+        else k_gs_step<3><<<grid, kThreads, 0, s>>>(L, T, coef, dinv, b, x, nsweeps, t, done);
         PDEOP_COUNT(1);
     }
     PDEOP_LAUNCH_CHECK();
@@ -335,7 +372,7 @@ __global__ void __launch_bounds__(kThreads) k_dense(LevelDev L, const double* __
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= L.G) return;
     const size_t n = (size_t)L.M * L.G;
-    dense_elem<D>(L, T + (size_t)blockIdx.y * L.D * kTabEntries * L.P, coef + (size_t)blockIdx.y * n,
+    dense_elem<D>(L, T + (size_t)blockIdx.y * L.D * kTabEntries * kTabPitch, coef + (size_t)blockIdx.y * n,
                   Kd + (size_t)blockIdx.y * n * n, w);
 }
 void be_dense(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, double* Kd) {
@@ -746,7 +783,28 @@ static void launch_syrk(cudaStream_t s, int B, int n, double* A, int r0, int r1,
 }
 
 // Band-limited: column k of L is nonzero only in rows [k, k+bw], so every update stops bw rows below its panel.
-void be_cholesky(stream_t st, int B, int n, int bw, double* Kd, FgmresState* state) {
+// Inverse of one kSolveBlk diagonal block of L (lower triangular): thread j builds column j by forward
+// substitution; L entries are warp-uniform (broadcast) reads, the column lives in the output (coalesced).
+__global__ void __launch_bounds__(kSolveBlk) k_trtri(int n, const double* __restrict__ Lf, size_t strideL,
+                                                     double* Linv, int nblk) {
+    const int kb = blockIdx.x, ib = blockIdx.y;
+    const int k0 = kb * kSolveBlk;
+    const int w = k0 + kSolveBlk < n ? kSolveBlk : n - k0;
+    const double* Lb = Lf + (size_t)ib * strideL + (size_t)k0 * n + k0;
+    double* Ib = Linv + ((size_t)ib * nblk + kb) * kSolveBlk * kSolveBlk;
+    const int j = threadIdx.x;
+    for (int i = 0; i < kSolveBlk; ++i) {
+        double v = 0.0;
+        if (j < w && i < w && i >= j) {
+            v = (i == j) ? 1.0 : 0.0;
+            for (int t = j; t < i; ++t) v -= Lb[(size_t)i * n + t] * Ib[(size_t)t * kSolveBlk + j];
+            v /= Lb[(size_t)i * n + i];
+        }
+        Ib[(size_t)i * kSolveBlk + j] = v;
+    }
+}
+
+void be_cholesky(stream_t st, int B, int n, int bw, double* Kd, double* Linv, FgmresState* state) {
     cudaStream_t s = (cudaStream_t)st;
     const size_t strideA = (size_t)n * n;
     for (int K0 = 0; K0 < n; K0 += kOuter) {
@@ -769,6 +827,9 @@ void be_cholesky(stream_t st, int B, int n, int bw, double* Kd, FgmresState* sta
         const int r1 = lim < n ? (int)lim : n;
         launch_syrk(s, B, n, Kd, K1, r1, K1, r1, K0, K1);
     }
+    const int nblk = (n + kSolveBlk - 1) / kSolveBlk;
+    k_trtri<<<dim3(nblk, B), kSolveBlk, 0, s>>>(n, Kd, strideA, Linv, nblk);
+    PDEOP_COUNT(1);
     PDEOP_LAUNCH_CHECK();
 }
 
@@ -776,13 +837,10 @@ void be_cholesky(stream_t st, int B, int n, int bw, double* Kd, FgmresState* sta
 // Blocked triangular solves  out = L^-T L^-1 rhs  (HBM-bound on L: each triangle is read once).
 // Block rows of kSolveBlk; per block: a GEMV with everything already solved + a small triangular solve.
 // =================================================================================================
-constexpr int kSolveBlk = 256;
-constexpr int kSolveSub = 64;
-
-// t[i] = r[i] - sum_{c<k0} L[i][c] y[c]   for rows i in [k0, k0+w): one warp per row
+// t[i] = r[i] - sum_{c in [c_lo,k0)} L[i][c] y[c]   for rows i in [k0, k0+w): one warp per row
 __global__ void __launch_bounds__(256) k_fwd_gemv(int n, const double* __restrict__ Lf, size_t strideL, int k0, int w,
-                                                  int c_lo, const double* __restrict__ r, const double* y,
-                                                  double* t, const int* done) {
+                                                  int c_lo, const double* r, const double* y, double* t,
+                                                  const int* done) {
     if (done && *done) return;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= w) return;
@@ -803,92 +861,64 @@ __global__ void __launch_bounds__(256) k_fwd_gemv(int n, const double* __restric
     if (lane == 0) t[(size_t)ib * n + k0 + row] = r[(size_t)ib * n + k0 + row] - a;
 }
 
-// solve L_kk y_k = t_k in place (t -> y) for the block [k0, k0+w): one CTA per instance
-__global__ void __launch_bounds__(256) k_fwd_diag(int n, const double* __restrict__ Lf, size_t strideL, int k0, int w,
-                                                  const double* t, double* y, const int* done) {
+// y_k = Linv_kk t_k  (lower triangular block): one warp per row
+__global__ void __launch_bounds__(256) k_blk_mv(int n, const double* __restrict__ Linv, int nblk, int kb, int w,
+                                                const double* t, double* y, const int* done) {
     if (done && *done) return;
-    __shared__ double Ls[kSolveSub][kSolveSub + 1];
+    __shared__ double ts[kSolveBlk];
+    const int ib = blockIdx.y;
+    const int k0 = kb * kSolveBlk;
+    for (int i = threadIdx.x; i < w; i += blockDim.x) ts[i] = t[(size_t)ib * n + k0 + i];
+    __syncthreads();
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= w) return;
+    const int lane = threadIdx.x & 31;
+    const double* Ir = Linv + ((size_t)ib * nblk + kb) * kSolveBlk * kSolveBlk + (size_t)row * kSolveBlk;
+    double a = 0.0;
+    for (int c = lane; c <= row; c += 32) a += Ir[c] * ts[c];
+    a = warp_sum(a);
+    if (lane == 0) y[(size_t)ib * n + k0 + row] = a;
+}
+
+// z_k = Linv_kk^T y_k : one thread per output i (coalesced along the rows of Linv); result goes to zout
+__global__ void __launch_bounds__(kSolveBlk) k_blk_mv_t(int n, const double* __restrict__ Linv, int nblk, int kb,
+                                                       int w, const double* y, double* zout, const int* done) {
+    if (done && *done) return;
     __shared__ double ys[kSolveBlk];
-    const int tid = threadIdx.x;
     const int ib = blockIdx.x;
-    const double* Lb = Lf + (size_t)ib * strideL;
-    for (int i = tid; i < w; i += blockDim.x) ys[i] = t[(size_t)ib * n + k0 + i];
-    for (int s0 = 0; s0 < w; s0 += kSolveSub) {
-        const int sw = s0 + kSolveSub < w ? kSolveSub : w - s0;
-        __syncthreads();
-        for (int idx = tid; idx < sw * sw; idx += blockDim.x) {
-            const int i = idx / sw, j = idx % sw;
-            Ls[i][j] = Lb[(size_t)(k0 + s0 + i) * n + k0 + s0 + j];
-        }
-        __syncthreads();
-        for (int j = 0; j < sw; ++j) {
-            if (tid == 0) ys[s0 + j] /= Ls[j][j];
-            __syncthreads();
-            const double yj = ys[s0 + j];
-            for (int i = j + 1 + tid; i < sw; i += blockDim.x) ys[s0 + i] -= Ls[i][j] * yj;
-            __syncthreads();
-        }
-        // rows of this block below the sub-block
-        for (int i = s0 + sw + tid; i < w; i += blockDim.x) {
-            const double* Lr = Lb + (size_t)(k0 + i) * n + k0 + s0;
-            double a = 0.0;
-            for (int j = 0; j < sw; ++j) a += Lr[j] * ys[s0 + j];
-            ys[i] -= a;
-        }
-    }
+    const int k0 = kb * kSolveBlk;
+    const int i = threadIdx.x;
+    if (i < w) ys[i] = y[(size_t)ib * n + k0 + i];
     __syncthreads();
-    for (int i = tid; i < w; i += blockDim.x) y[(size_t)ib * n + k0 + i] = ys[i];
+    if (i >= w) return;
+    const double* Ib = Linv + ((size_t)ib * nblk + kb) * kSolveBlk * kSolveBlk + i;
+    double a0 = 0.0, a1 = 0.0;
+    int r = i;
+    for (; r + 1 < w; r += 2) {
+        a0 += Ib[(size_t)r * kSolveBlk] * ys[r];
+        a1 += Ib[(size_t)(r + 1) * kSolveBlk] * ys[r + 1];
+    }
+    if (r < w) a0 += Ib[(size_t)r * kSolveBlk] * ys[r];
+    zout[(size_t)ib * n + k0 + i] = a0 + a1;
 }
 
-// solve L_kk^T z_k = y_k in place for the block [k0, k0+w)
-__global__ void __launch_bounds__(256) k_bwd_diag(int n, const double* __restrict__ Lf, size_t strideL, int k0, int w,
-                                                  double* __restrict__ y, const int* done) {
-    if (done && *done) return;
-    __shared__ double Ls[kSolveSub][kSolveSub + 1];
-    __shared__ double zs[kSolveBlk];
-    const int tid = threadIdx.x;
-    const int ib = blockIdx.x;
-    const double* Lb = Lf + (size_t)ib * strideL;
-    for (int i = tid; i < w; i += blockDim.x) zs[i] = y[(size_t)ib * n + k0 + i];
-    const int nsub = (w + kSolveSub - 1) / kSolveSub;
-    for (int sb = nsub - 1; sb >= 0; --sb) {
-        const int s0 = sb * kSolveSub;
-        const int sw = s0 + kSolveSub < w ? kSolveSub : w - s0;
-        __syncthreads();
-        for (int idx = tid; idx < sw * sw; idx += blockDim.x) {
-            const int i = idx / sw, j = idx % sw;
-            Ls[i][j] = Lb[(size_t)(k0 + s0 + i) * n + k0 + s0 + j];
-        }
-        __syncthreads();
-        for (int j = sw - 1; j >= 0; --j) {
-            if (tid == 0) zs[s0 + j] /= Ls[j][j];
-            __syncthreads();
-            const double zj = zs[s0 + j];
-            for (int i = tid; i < j; i += blockDim.x) zs[s0 + i] -= Ls[j][i] * zj;
-            __syncthreads();
-        }
-        // columns of this block left of the sub-block: z[c] -= sum_j L[s0+j][c] z[s0+j]
-        for (int c = tid; c < s0; c += blockDim.x) {
-            double a = 0.0;
-            for (int j = 0; j < sw; ++j) a += Lb[(size_t)(k0 + s0 + j) * n + k0 + c] * zs[s0 + j];
-            zs[c] -= a;
-        }
-    }
-    __syncthreads();
-    for (int i = tid; i < w; i += blockDim.x) y[(size_t)ib * n + k0 + i] = zs[i];
-}
-
-// y[c] -= sum_{r in [k0,k0+w)} L[r][c] z[r]  for c in [c_lo,k0): one thread per column (coalesced along rows of L)
+// y[c] -= sum_{r in [k0,k0+w)} L[r][c] z[r]  for c in [c_lo,k0) (one thread per column, coalesced along the rows
+// of L), and y[k0+i] = z[i] for the block itself; z = zsrc[k0..k0+w)
 __global__ void __launch_bounds__(256) k_bwd_update(int n, const double* __restrict__ Lf, size_t strideL, int k0,
-                                                    int w, int c_lo, double* __restrict__ y, const int* done) {
+                                                    int w, int c_lo, const double* __restrict__ zsrc, double* y,
+                                                    const int* done) {
     if (done && *done) return;
     __shared__ double zs[kSolveBlk];
     const int ib = blockIdx.y;
     double* yb = y + (size_t)ib * n;
-    for (int i = threadIdx.x; i < w; i += blockDim.x) zs[i] = yb[k0 + i];
+    for (int i = threadIdx.x; i < w; i += blockDim.x) zs[i] = zsrc[(size_t)ib * n + k0 + i];
     __syncthreads();
     const int c = c_lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= k0) return;
+    if (c >= k0 + w) return;
+    if (c >= k0) {
+        yb[c] = zs[c - k0];
+        return;
+    }
     const double* Lc = Lf + (size_t)ib * strideL + (size_t)k0 * n + c;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     int r = 0;
@@ -919,45 +949,43 @@ __global__ void __launch_bounds__(kThreads) k_from_band(LevelDev L, const double
     from_band_elem(L, bandv + o, wave + o, w);
 }
 
-void be_chol_solve(stream_t st, const LevelDev& L, int B, const double* Lf, const double* rhs, double* out,
-                   double* work, const int* done) {
+void be_chol_solve(stream_t st, const LevelDev& L, int B, const double* Lf, const double* Linv, const double* rhs,
+                   double* out, double* work, const int* done) {
     cudaStream_t s = (cudaStream_t)st;
     const int n = L.M * L.G;
     const int bw = L.bw;
     const size_t strideL = (size_t)n * n;
-    double* rb = work;                  // right-hand side in band ordering
-    double* y = work + (size_t)B * n;   // solution in band ordering, solved in place
+    const int nblk = (n + kSolveBlk - 1) / kSolveBlk;
+    double* rb = work;                  // right-hand side in band ordering; reused as block temporary
+    double* y = work + (size_t)B * n;   // solution in band ordering
     k_to_band<<<dim3(cdiv(L.G, kThreads), B), kThreads, 0, s>>>(L, rhs, rb, done);
     PDEOP_COUNT(1);
-    // forward: y = L^-1 rb
-    for (int k0 = 0; k0 < n; k0 += kSolveBlk) {
+    // forward: y = L^-1 rb.  Per block row: t = rb_k - L[k, band] y (GEMV, in place in rb), y_k = Linv_kk t
+    for (int kb = 0; kb < nblk; ++kb) {
+        const int k0 = kb * kSolveBlk;
         const int w = k0 + kSolveBlk < n ? kSolveBlk : n - k0;
-        const double* tsrc = rb;
         if (k0 > 0) {
             int c_lo = k0 - bw;
             if (c_lo < 0) c_lo = 0;
             c_lo &= ~31;
-            k_fwd_gemv<<<dim3(cdiv(w, 8), B), 256, 0, s>>>(n, Lf, strideL, k0, w, c_lo, rb, y, y, done);
+            k_fwd_gemv<<<dim3(cdiv(w, 8), B), 256, 0, s>>>(n, Lf, strideL, k0, w, c_lo, rb, y, rb, done);
             PDEOP_COUNT(1);
-            tsrc = y;
         }
-        k_fwd_diag<<<B, 256, 0, s>>>(n, Lf, strideL, k0, w, tsrc, y, done);
+        k_blk_mv<<<dim3(cdiv(w, 8), B), 256, 0, s>>>(n, Linv, nblk, kb, w, rb, y, done);
         PDEOP_COUNT(1);
     }
-    // backward: y = L^-T y, in place
-    const int nblk = (n + kSolveBlk - 1) / kSolveBlk;
+    // backward: y <- L^-T y.  Per block row (descending): z_k = Linv_kk^T y_k (into rb), then the update kernel
+    // stores z_k into y and subtracts L[k rows, c]^T z_k from the band columns left of the block
     for (int kb = nblk - 1; kb >= 0; --kb) {
         const int k0 = kb * kSolveBlk;
         const int w = k0 + kSolveBlk < n ? kSolveBlk : n - k0;
-        k_bwd_diag<<<B, 256, 0, s>>>(n, Lf, strideL, k0, w, y, done);
+        k_blk_mv_t<<<B, kSolveBlk, 0, s>>>(n, Linv, nblk, kb, w, y, rb, done);
         PDEOP_COUNT(1);
-        if (k0 > 0) {
-            int c_lo = k0 - bw;
-            if (c_lo < 0) c_lo = 0;
-            c_lo &= ~31;
-            k_bwd_update<<<dim3(cdiv(k0 - c_lo, 256), B), 256, 0, s>>>(n, Lf, strideL, k0, w, c_lo, y, done);
-            PDEOP_COUNT(1);
-        }
+        int c_lo = k0 - bw;
+        if (c_lo < 0) c_lo = 0;
+        c_lo &= ~31;
+        k_bwd_update<<<dim3(cdiv(k0 - c_lo + w, 256), B), 256, 0, s>>>(n, Lf, strideL, k0, w, c_lo, rb, y, done);
+        PDEOP_COUNT(1);
     }
     k_from_band<<<dim3(cdiv(L.G, kThreads), B), kThreads, 0, s>>>(L, y, out, done);
     PDEOP_COUNT(1);

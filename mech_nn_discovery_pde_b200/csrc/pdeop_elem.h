@@ -11,6 +11,7 @@
 //   linear grid transfer       solver/multigrid.py:243-268, 340-391 (F.interpolate, align_corners=True)
 //   gradients                  solver/qp_dual_sparse_multigrid_normal_kkt.py:112-162
 #pragma once
+#include <math.h>
 #include "pdeop_common.h"
 
 // Load policy for vectors that other thread blocks of the SAME kernel may be writing (the in-place
@@ -131,7 +132,7 @@ PDEOP_HD void build_table_elem(const LevelDev& L, int a, int ip, const double* c
             t[T_UU + 5] += g[0] * g[3];
         }
     }
-    for (int e = 0; e < kTabEntries; ++e) Ta[(size_t)e * L.P + ip] = t[e];
+    for (int e = 0; e < kTabEntries; ++e) Ta[(size_t)e * kTabPitch + ip] = t[e];
 }
 
 // wave index of the neighbour at offset o along internal axis AX
@@ -142,16 +143,23 @@ PDEOP_HD int neighbor_pos(const LevelDev& L, int s, int i0, int i1, int o) {
     return L.rowbase[(s + o + 4) * L.N[0] + i0 + o] + i1;
 }
 
+// table of (instance, active axis a): entry e of line position i is Tab(T,a)[e*kTabPitch + i + kTabPad]
+PDEOP_HD const double* axis_table(const double* T, int a) { return T + (size_t)a * kTabEntries * kTabPitch; }
+
 // ------------------------------------------------------------------------------------------------
 // acc[m] = sum over OFF-POINT couplings  K[(g,m),(g',m')] x[g',m'],  g' = g + o e_a, o in [-4,4]\{0}
-// T: instance tables [D][30][P];  x: instance vector [M][G]
+// T: instance tables [D][30][kTabPitch];  x: instance vector [M][G].
+// Branch-free: out-of-range neighbours are predicated loads (value 0); their coefficients are exact zeros
+// because the tables are zero-padded by 4 positions on either side.  All table loads are
+// [position pointer + compile-time offset]; vector loads use one pointer per channel plane and axis.
 // ------------------------------------------------------------------------------------------------
 template <int D, class LD>
-PDEOP_HD void k_neighbors(const LevelDev& L, const double* __restrict__ T, const double* x, int i0,
-                          int i1, int i2, double acc[1 + 2 * D]) {
-    const int G = L.G, P = L.P;
-    const int s = i0 + i1 + i2;
+PDEOP_HD void k_neighbors(const LevelDev& L, const double* __restrict__ T, const double* x, int i0, int i1, int i2,
+                          double acc[1 + 2 * D]) {
+    const int G = L.G, N0 = L.N[0];
     const int idx[3] = {i0, i1, i2};
+    // rb[o*N0] = rowbase[s+o][i0],  rb[o*N0 + o] = rowbase[s+o][i0+o]
+    const int* __restrict__ rb = L.rowbase + (i0 + i1 + i2 + 4) * N0 + i0;
 #pragma unroll
     for (int m = 0; m < 1 + 2 * D; ++m) acc[m] = 0.0;
 #pragma unroll
@@ -159,23 +167,28 @@ PDEOP_HD void k_neighbors(const LevelDev& L, const double* __restrict__ T, const
         const int ax = 3 - D + a;
         const int n = L.N[ax];
         const int i = idx[ax];
-        const double* __restrict__ Ta = T + (size_t)a * kTabEntries * P + (i + kTabPad);
+        const double* __restrict__ Ta = axis_table(T, a) + (i + kTabPad);
+        const double* xu = x;
+        const double* xp = x + (1 + a) * G;
+        const double* xq = x + (1 + D + a) * G;
         double au = 0.0, ap = 0.0, aq = 0.0;
 #pragma unroll
         for (int o = -4; o <= 4; ++o) {
             if (o == 0) continue;
-            const int ii = i + o;
-            if (ii < 0 || ii >= n) continue;
+            const bool ok = (unsigned)(i + o) < (unsigned)n;
             int wn;
-            if (ax == 2) wn = neighbor_pos<2>(L, s, i0, i1, o);
-            else if (ax == 1) wn = neighbor_pos<1>(L, s, i0, i1, o);
-            else wn = neighbor_pos<0>(L, s, i0, i1, o);
-            const double un = LD::ld(x + wn);
-            const double pn = LD::ld(x + (size_t)(1 + a) * G + wn);
-            const double qn = LD::ld(x + (size_t)(1 + D + a) * G + wn);
-            au += Ta[(T_UU + o + 4) * P] * un + Ta[(T_UP - o + 4) * P + o] * pn + Ta[(T_UQ - o + 4) * P + o] * qn;
-            ap += Ta[(T_UP + o + 4) * P] * un;
-            aq += Ta[(T_UQ + o + 4) * P] * un;
+            if (ax == 2) wn = rb[o * N0] + i1;
+            else if (ax == 1) wn = rb[o * N0] + i1 + o;
+            else wn = rb[o * N0 + o] + i1;
+            const double un = ok ? LD::ld(xu + wn) : 0.0;
+            const double pn = ok ? LD::ld(xp + wn) : 0.0;
+            const double qn = ok ? LD::ld(xq + wn) : 0.0;
+            // explicit fma: the same bits from every kernel that inlines this body (and from the host emulator)
+            au = fma(Ta[(T_UU + o + 4) * kTabPitch], un, au);
+            au = fma(Ta[(T_UP - o + 4) * kTabPitch + o], pn, au);
+            au = fma(Ta[(T_UQ - o + 4) * kTabPitch + o], qn, au);
+            ap = fma(Ta[(T_UP + o + 4) * kTabPitch], un, ap);
+            aq = fma(Ta[(T_UQ + o + 4) * kTabPitch], un, aq);
         }
         acc[0] += au;
         acc[1 + a] += ap;
@@ -194,28 +207,54 @@ struct PointLocal {
 };
 
 template <int D>
-PDEOP_HD void load_local(const LevelDev& L, const double* __restrict__ T, const double* __restrict__ coef, int w,
-                         int i0, int i1, int i2, int flags, PointLocal<D>& pl) {
-    const int G = L.G, P = L.P;
+PDEOP_HD void load_axis_local(const double* __restrict__ T, int i0, int i1, int i2, PointLocal<D>& pl) {
     const int idx[3] = {i0, i1, i2};
-    const bool eq = flags & 1;
-#pragma unroll
-    for (int m = 0; m < 1 + 2 * D; ++m) {
-        pl.c[m] = eq ? coef[(size_t)m * G + w] : 0.0;
-        pl.ini[m] = (double)((flags >> (4 + 2 * m)) & 3);
-    }
     pl.uu = 0.0;
 #pragma unroll
     for (int a = 0; a < D; ++a) {
-        const int i = idx[3 - D + a];
-        const double* __restrict__ Ta = T + (size_t)a * kTabEntries * P + (i + kTabPad);
-        pl.uu += Ta[(T_UU + 4) * P];
-        pl.up[a] = Ta[(T_UP + 4) * P];
-        pl.uq[a] = Ta[(T_UQ + 4) * P];
-        pl.pp[a] = Ta[T_PP * P];
-        pl.qq[a] = Ta[T_QQ * P];
-        pl.pq[a] = Ta[T_PQ * P];
+        const double* __restrict__ Ta = axis_table(T, a) + (idx[3 - D + a] + kTabPad);
+        pl.uu += Ta[(T_UU + 4) * kTabPitch];
+        pl.up[a] = Ta[(T_UP + 4) * kTabPitch];
+        pl.uq[a] = Ta[(T_UQ + 4) * kTabPitch];
+        pl.pp[a] = Ta[T_PP * kTabPitch];
+        pl.qq[a] = Ta[T_QQ * kTabPitch];
+        pl.pq[a] = Ta[T_PQ * kTabPitch];
     }
+}
+
+template <int D>
+PDEOP_HD void load_local(const LevelDev& L, const double* __restrict__ T, const double* __restrict__ coef, int w,
+                         int i0, int i1, int i2, int flags, PointLocal<D>& pl) {
+    const int G = L.G;
+    const bool eq = flags & 1;
+#pragma unroll
+    for (int m = 0; m < 1 + 2 * D; ++m) {
+        pl.c[m] = eq ? coef[m * G + w] : 0.0;
+        pl.ini[m] = (double)((flags >> (4 + 2 * m)) & 3);
+    }
+    load_axis_local<D>(T, i0, i1, i2, pl);
+}
+
+// diagonal of K at channel m of a point
+template <int D>
+PDEOP_HD double k_diag(const PointLocal<D>& pl, int m) {
+    double d = pl.c[m] * pl.c[m] + pl.ini[m];
+    if (m == 0) d += pl.uu;
+    else if (m <= D) d += pl.pp[m - 1];
+    else d += pl.qq[m - 1 - D];
+    return d;
+}
+
+// dinv[m][w] = 1 / K[(w,m),(w,m)]
+template <int D>
+PDEOP_HD void dinv_elem(const LevelDev& L, const double* __restrict__ T, const double* __restrict__ coef,
+                        double* __restrict__ dinv, int w) {
+    int i0, i1, i2;
+    unpack_coord(L.coord[w], i0, i1, i2);
+    PointLocal<D> pl;
+    load_local<D>(L, T, coef, w, i0, i1, i2, L.flags[w], pl);
+#pragma unroll
+    for (int m = 0; m < 1 + 2 * D; ++m) dinv[m * L.G + w] = 1.0 / k_diag<D>(pl, m);
 }
 
 // y = K x at one point (mode 0) or y = b - K x (mode 1)
@@ -236,7 +275,7 @@ PDEOP_HD void apply_k_elem(const LevelDev& L, const double* __restrict__ T, cons
     double cs = 0.0;
 #pragma unroll
     for (int m = 0; m < M; ++m) {
-        xl[m] = x[(size_t)m * G + w];
+        xl[m] = x[m * G + w];
         cs += pl.c[m] * xl[m];
     }
     double yl[M];
@@ -251,56 +290,61 @@ PDEOP_HD void apply_k_elem(const LevelDev& L, const double* __restrict__ T, cons
     }
 #pragma unroll
     for (int m = 0; m < M; ++m) {
-        const size_t k = (size_t)m * G + w;
+        const int k = m * G + w;
         y[k] = mode ? (b[k] - yl[m]) : yl[m];
     }
 }
 
 // One lexicographic Gauss-Seidel update of the M unknowns of point w (channel order 0..M-1):
 //   x_j <- (b_j - sum_{k != j} K_jk x_k) / K_jj   with already-updated values for k < j.
+// The equation-row part of the point block is rank one (c c^T): the running sum S = c.x is kept up to
+// date as channels are updated, and the division is a multiplication by the precomputed reciprocal diagonal.
 template <int D, class LD>
 PDEOP_HD void gs_elem(const LevelDev& L, const double* __restrict__ T, const double* __restrict__ coef,
-                      const double* __restrict__ b, double* x, int w) {
+                      const double* __restrict__ dinv, const double* __restrict__ b, double* x, int w) {
     constexpr int M = 1 + 2 * D;
     const int G = L.G;
     int i0, i1, i2;
     unpack_coord(L.coord[w], i0, i1, i2);
-    const int flags = L.flags[w];
+    const bool eq = L.flags[w] & 1;
     double acc[M];
     k_neighbors<D, LD>(L, T, x, i0, i1, i2, acc);
     PointLocal<D> pl;
-    load_local<D>(L, T, coef, w, i0, i1, i2, flags, pl);
-    double xl[M], r[M];
+    load_axis_local<D>(T, i0, i1, i2, pl);
+    double xl[M], c[M];
+    double S = 0.0;
 #pragma unroll
     for (int m = 0; m < M; ++m) {
-        xl[m] = LD::ld(x + (size_t)m * G + w);
-        r[m] = b[(size_t)m * G + w] - acc[m];
+        xl[m] = LD::ld(x + m * G + w);
+        c[m] = eq ? coef[m * G + w] : 0.0;
+        acc[m] = b[m * G + w] - acc[m];
+        S = fma(c[m], xl[m], S);
     }
 #pragma unroll
     for (int m = 0; m < M; ++m) {
-        double t = 0.0;
-#pragma unroll
-        for (int k = 0; k < M; ++k)
-            if (k != m) t += pl.c[k] * xl[k];
-        double off = pl.c[m] * t;
-        double diag = pl.c[m] * pl.c[m] + pl.ini[m];
+        const double t = fma(-c[m], xl[m], S);      // sum_{k != m} c_k x_k
+        double off = c[m] * t;
         if (m == 0) {
-            diag += pl.uu;
 #pragma unroll
-            for (int a = 0; a < D; ++a) off += pl.up[a] * xl[1 + a] + pl.uq[a] * xl[1 + D + a];
+            for (int a = 0; a < D; ++a) {
+                off = fma(pl.up[a], xl[1 + a], off);
+                off = fma(pl.uq[a], xl[1 + D + a], off);
+            }
         } else if (m <= D) {
             const int a = m - 1;
-            diag += pl.pp[a];
-            off += pl.up[a] * xl[0] + pl.pq[a] * xl[1 + D + a];
+            off = fma(pl.up[a], xl[0], off);
+            off = fma(pl.pq[a], xl[1 + D + a], off);
         } else {
             const int a = m - 1 - D;
-            diag += pl.qq[a];
-            off += pl.uq[a] * xl[0] + pl.pq[a] * xl[1 + a];
+            off = fma(pl.uq[a], xl[0], off);
+            off = fma(pl.pq[a], xl[1 + a], off);
         }
-        xl[m] = (r[m] - off) / diag;
+        const double xn = (acc[m] - off) * dinv[m * G + w];
+        S = fma(c[m], xn, t);
+        xl[m] = xn;
     }
 #pragma unroll
-    for (int m = 0; m < M; ++m) x[(size_t)m * G + w] = xl[m];
+    for (int m = 0; m < M; ++m) x[m * G + w] = xl[m];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -378,7 +422,8 @@ template <int D>
 PDEOP_HD void dense_elem(const LevelDev& L, const double* __restrict__ T, const double* __restrict__ coef,
                          double* __restrict__ Kd, int w) {
     constexpr int M = 1 + 2 * D;
-    const int G = L.G, P = L.P;
+    const int G = L.G;
+    constexpr int P = kTabPitch;
     const size_t n = (size_t)M * G;
     int i0, i1, i2;
     unpack_coord(L.coord[w], i0, i1, i2);
@@ -412,7 +457,7 @@ PDEOP_HD void dense_elem(const LevelDev& L, const double* __restrict__ T, const 
         const int ax = 3 - D + a;
         const int nn = L.N[ax];
         const int i = idx[ax];
-        const double* Ta = T + (size_t)a * kTabEntries * P + (i + kTabPad);
+        const double* Ta = axis_table(T, a) + (i + kTabPad);
         const size_t ru = r0, rp = r0 + 1 + a, rq = r0 + 1 + D + a;
         for (int o = -4; o <= 4; ++o) {
             if (o == 0) continue;

@@ -69,7 +69,7 @@ static int fail(const std::string& msg) {
 struct LevelHost {
     LevelDev dev;
     std::vector<void*> owned;  // device allocations
-    size_t off_T = 0, off_coef = 0;        // persist offsets (doubles)
+    size_t off_T = 0, off_coef = 0, off_dinv = 0;   // persist offsets (doubles)
     size_t off_x = 0, off_b = 0, off_r = 0;  // scratch offsets (doubles), levels >= 1
 };
 
@@ -78,6 +78,7 @@ struct pdeop_plan {
     std::vector<LevelHost> lev;
     size_t persist_doubles = 0;
     size_t off_Kd = 0;  // persist offset of the coarsest dense matrix / factor
+    size_t off_Linv = 0;  // persist offset of the inverse diagonal blocks of the factor
     int nc = 0;         // coarsest unknowns per instance
 };
 
@@ -102,7 +103,8 @@ static int build_level(pdeop_plan* pl, LevelHost& lh, const int* dims, int n_iv,
     L.M = 1 + 2 * D;
     L.G = L.N[0] * L.N[1] * L.N[2];
     L.S = L.N[0] + L.N[1] + L.N[2] - 2;
-    L.P = std::max(L.N[0], std::max(L.N[1], L.N[2])) + 2 * kTabPad;
+    L.P = kTabPitch;
+    if ((long long)L.M * L.G >= (1LL << 31)) return fail("grid too large for 32-bit vector indexing");
     L.Ntot = 0;
     L.Ftot = 0;
     for (int c = 0; c < D; ++c) {
@@ -113,7 +115,7 @@ static int build_level(pdeop_plan* pl, LevelHost& lh, const int* dims, int n_iv,
         L.Ftot += dims[c] - 1;
     }
     const int N0 = L.N[0], N1 = L.N[1], N2 = L.N[2];
-    std::vector<int> coord(L.G), flags(L.G, 0), hstart(L.S + 1), rowbase((size_t)(L.S + 8) * N0, 0);
+    std::vector<int> coord(L.G), flags(L.G, 0), hstart(L.S + 1), rowbase((size_t)(L.S + 8) * N0 + 8, 0);
     std::vector<int> nat2wave(L.G);
     int w = 0;
     for (int s = 0; s < L.S; ++s) {
@@ -121,7 +123,7 @@ static int build_level(pdeop_plan* pl, LevelHost& lh, const int* dims, int n_iv,
         for (int i0 = 0; i0 < N0; ++i0) {
             int lo = std::max(0, s - i0 - (N2 - 1));
             int hi = std::min(N1 - 1, s - i0);
-            rowbase[(size_t)(s + 4) * N0 + i0] = w - lo;
+            rowbase[4 + (size_t)(s + 4) * N0 + i0] = w - lo;
             for (int i1 = lo; i1 <= hi; ++i1) {
                 int i2 = s - i0 - i1;
                 coord[w] = i0 | (i1 << 10) | (i2 << 20);
@@ -191,7 +193,7 @@ static int build_level(pdeop_plan* pl, LevelHost& lh, const int* dims, int n_iv,
     L.coord = upload_vec(lh, coord);
     L.flags = upload_vec(lh, flags);
     L.hstart = upload_vec(lh, hstart);
-    L.rowbase = upload_vec(lh, rowbase);
+    L.rowbase = upload_vec(lh, rowbase) + 4;   // 4 spare ints either side: branch-free neighbour lookups
     L.init_w = upload_vec(lh, init_w);
     L.init_m = upload_vec(lh, init_m);
     return 0;
@@ -226,6 +228,8 @@ extern "C" int pdeop_plan_create(int d, const int* dims, int order, int batch, i
         poff += (size_t)batch * d * kTabEntries * L.P;
         lh.off_coef = poff;
         poff += (size_t)batch * L.M * L.G;
+        lh.off_dinv = poff;
+        poff += (size_t)batch * L.M * L.G;
         for (int c = 0; c < d; ++c)  // multigrid.py:99-102
             if (c > 0 || downsample_first) cur[c] /= 2;
     }
@@ -233,6 +237,8 @@ extern "C" int pdeop_plan_create(int d, const int* dims, int order, int batch, i
     pl->nc = Lc.M * Lc.G;
     pl->off_Kd = poff;
     poff += (size_t)batch * pl->nc * pl->nc;
+    pl->off_Linv = poff;
+    poff += (size_t)batch * ((pl->nc + kSolveBlk - 1) / kSolveBlk) * kSolveBlk * kSolveBlk;
     pl->persist_doubles = poff;
     *out = pl;
     return 0;
@@ -325,7 +331,9 @@ static int check_backend() {
 
 static double* P_T(const pdeop_plan* pl, void* persist, int l) { return (double*)persist + pl->lev[l].off_T; }
 static double* P_coef(const pdeop_plan* pl, void* persist, int l) { return (double*)persist + pl->lev[l].off_coef; }
+static double* P_dinv(const pdeop_plan* pl, void* persist, int l) { return (double*)persist + pl->lev[l].off_dinv; }
 static double* P_Kd(const pdeop_plan* pl, void* persist) { return (double*)persist + pl->off_Kd; }
+static double* P_Linv(const pdeop_plan* pl, void* persist) { return (double*)persist + pl->off_Linv; }
 
 // Operator set-up: level-0 coefficients into wave layout, coarse coefficients by linear interpolation
 // of the finer level's (multigrid.py:243-256), axis tables of every level from that level's line
@@ -343,6 +351,7 @@ static void setup_operator(pdeop_plan* pl, const double* coeffs, const double* c
                 be_interp(st, pl->lev[l - 1].dev, L, B, L.M, P_coef(pl, persist, l - 1), P_coef(pl, persist, l), 0,
                           nullptr);
             be_build_tables(st, L, B, cv[l], fv[l], bv[l], P_T(pl, persist, l));
+            be_dinv(st, L, B, P_T(pl, persist, l), P_coef(pl, persist, l), P_dinv(pl, persist, l));
         }
         const int lc = pl->n_grid - 1;
         double* Kd = P_Kd(pl, persist);
@@ -350,7 +359,7 @@ static void setup_operator(pdeop_plan* pl, const double* coeffs, const double* c
         be_dense(st, pl->lev[lc].dev, B, P_T(pl, persist, lc), P_coef(pl, persist, lc), Kd);
     }
     ProfScope pf(PC_FACTOR, st);
-    be_cholesky(st, B, pl->nc, pl->lev[pl->n_grid - 1].dev.bw, P_Kd(pl, persist), sc.state);
+    be_cholesky(st, B, pl->nc, pl->lev[pl->n_grid - 1].dev.bw, P_Kd(pl, persist), P_Linv(pl, persist), sc.state);
 }
 
 static void vcycle(pdeop_plan* pl, const pdeop_solver_cfg* cfg, void* persist, Scratch& sc, int l, const double* b,
@@ -360,7 +369,8 @@ static void vcycle(pdeop_plan* pl, const pdeop_solver_cfg* cfg, void* persist, S
     const int* done = &sc.state->done;
     {
         ProfScope ps(l == 0 ? PC_GS_FINE : PC_GS_COARSE, st);
-        be_gs(st, L, B, P_T(pl, persist, l), P_coef(pl, persist, l), b, x, cfg->gs_pre, done, cfg->gs_variant);
+        be_gs(st, L, B, P_T(pl, persist, l), P_coef(pl, persist, l), P_dinv(pl, persist, l), b, x, cfg->gs_pre, done,
+              cfg->gs_variant);
     }
     {
         ProfScope ps(l == 0 ? PC_APPLY_FINE : PC_APPLY_COARSE, st);
@@ -373,7 +383,7 @@ static void vcycle(pdeop_plan* pl, const pdeop_solver_cfg* cfg, void* persist, S
     }
     if (l + 1 == pl->n_grid - 1) {
         ProfScope ps(PC_COARSE_SOLVE, st);
-        be_chol_solve(st, Lc, B, P_Kd(pl, persist), sc.lb[l + 1], sc.lx[l + 1], sc.cwork, done);
+        be_chol_solve(st, Lc, B, P_Kd(pl, persist), P_Linv(pl, persist), sc.lb[l + 1], sc.lx[l + 1], sc.cwork, done);
     } else {
         be_zero(st, sc.lx[l + 1], (size_t)B * Lc.M * Lc.G * sizeof(double));
         vcycle(pl, cfg, persist, sc, l + 1, sc.lb[l + 1], sc.lx[l + 1], sc.lr[l + 1], st);
@@ -383,7 +393,8 @@ static void vcycle(pdeop_plan* pl, const pdeop_solver_cfg* cfg, void* persist, S
         be_interp(st, Lc, L, B, L.M, sc.lx[l + 1], x, 1, done);
     }
     ProfScope ps(l == 0 ? PC_GS_FINE : PC_GS_COARSE, st);
-    be_gs(st, L, B, P_T(pl, persist, l), P_coef(pl, persist, l), b, x, cfg->gs_post, done, cfg->gs_variant);
+    be_gs(st, L, B, P_T(pl, persist, l), P_coef(pl, persist, l), P_dinv(pl, persist, l), b, x, cfg->gs_post, done,
+          cfg->gs_variant);
 }
 
 // z = V-cycle(b) from a zero initial guess (multigrid.py:490-498)
@@ -509,7 +520,7 @@ extern "C" int pdeop_dense_forward(pdeop_plan* pl, const double* coeffs, const d
     const double* bvp[1] = {bv0};
     setup_operator(pl, coeffs, cvp, fvp, bvp, persist, sc, stream);
     be_atb(stream, pl->lev[0].dev, pl->B, P_coef(pl, persist, 0), rhs, iv_rhs, sc.atb);
-    be_chol_solve(stream, pl->lev[0].dev, pl->B, P_Kd(pl, persist), sc.atb, sc.x, sc.cwork, nullptr);
+    be_chol_solve(stream, pl->lev[0].dev, pl->B, P_Kd(pl, persist), P_Linv(pl, persist), sc.atb, sc.x, sc.cwork, nullptr);
     be_unpack(stream, pl->lev[0].dev, pl->B, sc.x, x_out);
     if (info_out) be_fg_info(stream, sc.state, info_out);
     return check_backend();
@@ -524,7 +535,7 @@ extern "C" int pdeop_dense_backward(pdeop_plan* pl, const double* rhs, const dou
     Scratch sc = carve(pl, scratch, 1);
     be_state_reset(stream, sc.state);
     be_pack(stream, pl->lev[0].dev, pl->B, grad_x, sc.atb);
-    be_chol_solve(stream, pl->lev[0].dev, pl->B, P_Kd(pl, persist), sc.atb, sc.x, sc.cwork, nullptr);  // dz (:65)
+    be_chol_solve(stream, pl->lev[0].dev, pl->B, P_Kd(pl, persist), P_Linv(pl, persist), sc.atb, sc.x, sc.cwork, nullptr);  // dz (:65)
     if (info_out) be_fg_info(stream, sc.state, info_out);
     run_grads(pl, persist, sc, rhs, cv0, fv0, bv0, x, sc.x, d_coeffs, d_rhs, d_iv_rhs, d_cv, d_fv, d_bv, stream);
     return check_backend();
@@ -568,8 +579,8 @@ extern "C" int pdeop_stage(pdeop_plan* pl, const pdeop_solver_cfg* cfg, int stag
         case PDEOP_STAGE_GS:
             be_pack(stream, L, B, in1, t1);
             be_pack(stream, L, B, in2, t2);
-            be_gs(stream, L, B, P_T(pl, persist, level), P_coef(pl, persist, level), t1, t2, count, nullptr,
-                  cfg->gs_variant);
+            be_gs(stream, L, B, P_T(pl, persist, level), P_coef(pl, persist, level), P_dinv(pl, persist, level), t1, t2,
+                  count, nullptr, cfg->gs_variant);
             be_unpack(stream, L, B, t2, out);
             break;
         case PDEOP_STAGE_RESTRICT: {
@@ -598,7 +609,7 @@ extern "C" int pdeop_stage(pdeop_plan* pl, const pdeop_solver_cfg* cfg, int stag
         case PDEOP_STAGE_COARSE_SOLVE:
             if (level != pl->n_grid - 1) return fail("coarse solve runs on the last level");
             be_pack(stream, L, B, in1, t1);
-            be_chol_solve(stream, L, B, P_Kd(pl, persist), t1, t2, sc.cwork, nullptr);
+            be_chol_solve(stream, L, B, P_Kd(pl, persist), P_Linv(pl, persist), t1, t2, sc.cwork, nullptr);
             be_unpack(stream, L, B, t2, out);
             break;
         case PDEOP_STAGE_ATB:

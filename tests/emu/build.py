@@ -14,7 +14,7 @@ def build(force=False):
         [os.path.join(ROOT, "include", "pdeop.h")]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
         return OUT
-    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", OUT] + SRC
+    cmd = ["g++", "-O2", "-mfma", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-o", OUT] + SRC
     subprocess.check_call(cmd)
     return OUT
 

@@ -33,7 +33,7 @@ float be_event_elapsed_ms(void*, void*) { return 0.f; }
 long long be_launch_count() { return 0; }
 
 static inline size_t vstride(const LevelDev& L) { return (size_t)L.M * L.G; }
-static inline size_t tstride(const LevelDev& L) { return (size_t)L.D * kTabEntries * L.P; }
+static inline size_t tstride(const LevelDev& L) { return (size_t)L.D * kTabEntries * kTabPitch; }
 
 void be_build_tables(stream_t, const LevelDev& L, int B, const double* cv, const double* fv, const double* bv,
                      double* T) {
@@ -41,7 +41,7 @@ void be_build_tables(stream_t, const LevelDev& L, int B, const double* cv, const
         for (int a = 0; a < L.D; ++a)
             for (int ip = 0; ip < L.P; ++ip)
                 build_table_elem(L, a, ip, cv + (size_t)b * L.Ntot * 12, fv + (size_t)b * L.Ftot * 4,
-                                 bv + (size_t)b * L.Ftot * 4, T + b * tstride(L) + (size_t)a * kTabEntries * L.P);
+                                 bv + (size_t)b * L.Ftot * 4, T + b * tstride(L) + (size_t)a * kTabEntries * kTabPitch);
 }
 
 void be_pack(stream_t, const LevelDev& L, int B, const double* api, double* wave) {
@@ -88,8 +88,8 @@ void be_apply_k(stream_t, const LevelDev& L, int B, const double* T, const doubl
 }
 
 template <int D>
-static void gs_t(const LevelDev& L, int B, const double* T, const double* coef, const double* b, double* x,
-                 int nsweeps) {
+static void gs_t(const LevelDev& L, int B, const double* T, const double* coef, const double* dinv, const double* b,
+                 double* x, int nsweeps) {
     std::vector<int> hs(L.S + 1);
     memcpy(hs.data(), L.hstart, sizeof(int) * (L.S + 1));
     const int steps = L.S + kGsLag * (nsweeps - 1);
@@ -100,18 +100,27 @@ static void gs_t(const LevelDev& L, int B, const double* T, const double* coef, 
                 const int s = t - kGsLag * k;
                 if (s < 0 || s >= L.S) continue;
                 for (int w = hs[s]; w < hs[s + 1]; ++w)
-                    gs_elem<D, LdPlain>(L, T + ib * tstride(L), coef + ib * vstride(L), b + ib * vstride(L),
-                               x + ib * vstride(L), w);
+                    gs_elem<D, LdPlain>(L, T + ib * tstride(L), coef + ib * vstride(L), dinv + ib * vstride(L),
+                                        b + ib * vstride(L), x + ib * vstride(L), w);
             }
 }
 
-void be_gs(stream_t, const LevelDev& L, int B, const double* T, const double* coef, const double* b, double* x,
-           int nsweeps, const int* done, int) {
+void be_gs(stream_t, const LevelDev& L, int B, const double* T, const double* coef, const double* dinv,
+           const double* b, double* x, int nsweeps, const int* done, int) {
     if (done && *done) return;
     if (nsweeps <= 0) return;
-    if (L.D == 1) gs_t<1>(L, B, T, coef, b, x, nsweeps);
-    else if (L.D == 2) gs_t<2>(L, B, T, coef, b, x, nsweeps);
-    else gs_t<3>(L, B, T, coef, b, x, nsweeps);
+    if (L.D == 1) gs_t<1>(L, B, T, coef, dinv, b, x, nsweeps);
+    else if (L.D == 2) gs_t<2>(L, B, T, coef, dinv, b, x, nsweeps);
+    else gs_t<3>(L, B, T, coef, dinv, b, x, nsweeps);
+}
+
+void be_dinv(stream_t, const LevelDev& L, int B, const double* T, const double* coef, double* dinv) {
+    for (int ib = 0; ib < B; ++ib)
+        for (int w = 0; w < L.G; ++w) {
+            if (L.D == 1) dinv_elem<1>(L, T + ib * tstride(L), coef + ib * vstride(L), dinv + ib * vstride(L), w);
+            else if (L.D == 2) dinv_elem<2>(L, T + ib * tstride(L), coef + ib * vstride(L), dinv + ib * vstride(L), w);
+            else dinv_elem<3>(L, T + ib * tstride(L), coef + ib * vstride(L), dinv + ib * vstride(L), w);
+        }
 }
 
 void be_dense(stream_t, const LevelDev& L, int B, const double* T, const double* coef, double* Kd) {
@@ -124,7 +133,7 @@ void be_dense(stream_t, const LevelDev& L, int B, const double* T, const double*
         }
 }
 
-void be_cholesky(stream_t, int B, int n, int, double* Kd, FgmresState* state) {
+void be_cholesky(stream_t, int B, int n, int, double* Kd, double*, FgmresState* state) {
     for (int ib = 0; ib < B; ++ib) {
         double* A = Kd + (size_t)ib * n * n;
         for (int j = 0; j < n; ++j) {
@@ -145,8 +154,8 @@ void be_cholesky(stream_t, int B, int n, int, double* Kd, FgmresState* state) {
     }
 }
 
-void be_chol_solve(stream_t, const LevelDev& L, int B, const double* Lf, const double* rhs, double* out, double* work,
-                   const int* done) {
+void be_chol_solve(stream_t, const LevelDev& L, int B, const double* Lf, const double*, const double* rhs, double* out,
+                   double* work, const int* done) {
     if (done && *done) return;
     const int n = L.M * L.G;
     for (int ib = 0; ib < B; ++ib) {
