@@ -190,15 +190,18 @@ void be_apply_k(stream_t st, const LevelDev& L, int B, const double* T, const do
 // then the cluster barrier (release/acquire) orders the in-place iterate for the next step.
 // The iterate is read at the L2 coherence point (LdL2) because other CTAs of the cluster write it.
 // =================================================================================================
-constexpr int kGsMaxSweeps = 16;
-
-template <int D, int THREADS, class LD>
-__global__ void __launch_bounds__(THREADS, 1) k_gs_cluster(LevelDev L, const double* __restrict__ T,
-                                                           const double* __restrict__ coef,
-                                                           const double* __restrict__ dinv,
-                                                           const double* __restrict__ b, double* x, int nsweeps,
-                                                           const int* done) {
+// PS > 0: the instance's K tables are staged in shared memory with compile-time pitch PS (max extent + 8 <= PS),
+// together with the level's rowbase/hstart index tables: the cluster barrier invalidates L1 every step, so
+// anything read from global memory is re-fetched from L2 each step, while shared memory stays put.
+// PS == 0: tables too large for shared memory, read from global memory.
+template <int D, int THREADS, int MINB, class LD, int PS, bool PF>
+__global__ void __launch_bounds__(THREADS, MINB) k_gs_cluster(LevelDev L, const double* __restrict__ T,
+                                                              const double* __restrict__ coef,
+                                                              const double* __restrict__ dinv,
+                                                              const double* __restrict__ b, double* x, int nsweeps,
+                                                              const int* done) {
     if (done && *done) return;
+    extern __shared__ __align__(16) unsigned char gs_smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int csize = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
@@ -207,6 +210,28 @@ __global__ void __launch_bounds__(THREADS, 1) k_gs_cluster(LevelDev L, const dou
     const int nthreads = csize * blockDim.x;
     const size_t o = (size_t)ib * L.M * L.G;
     const double* Ti = T + (size_t)ib * L.D * kTabEntries * kTabPitch;
+    constexpr int PITCH = PS > 0 ? PS : kTabPitch;
+    const double* Tuse = Ti;
+    const int* rbuse = L.rowbase;
+    const int* hs = L.hstart;
+    if (PS > 0) {
+        double* Ts = reinterpret_cast<double*>(gs_smem);
+        int* rbs = reinterpret_cast<int*>(Ts + D * kTabEntries * PS);
+        const int nrb = (L.S + 8) * L.N[0] + 8;
+        int* hss = rbs + nrb;
+        int maxn = L.N[0] > L.N[1] ? L.N[0] : L.N[1];
+        maxn = (maxn > L.N[2] ? maxn : L.N[2]) + 2 * kTabPad;
+        for (int i = threadIdx.x; i < D * kTabEntries * PS; i += blockDim.x) {
+            const int row = i / PS, pos = i - row * PS;
+            Ts[i] = pos < maxn ? Ti[(size_t)row * kTabPitch + pos] : 0.0;
+        }
+        for (int i = threadIdx.x; i < nrb; i += blockDim.x) rbs[i] = L.rowbase[i - 4];
+        for (int i = threadIdx.x; i <= L.S; i += blockDim.x) hss[i] = L.hstart[i];
+        __syncthreads();
+        Tuse = Ts;
+        rbuse = rbs + 4;
+        hs = hss;
+    }
     const int steps = L.S + kGsLag * (nsweeps - 1);
     for (int t = 0; t < steps; ++t) {
         // active hyperplanes of this step: s_k = t - lag*k for sweep k
@@ -217,20 +242,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_gs_cluster(LevelDev L, const dou
         int total = 0;
         for (int k = k_lo; k <= k_hi; ++k) {
             const int s = t - kGsLag * k;
-            total += L.hstart[s + 1] - L.hstart[s];
+            total += hs[s + 1] - hs[s];
         }
         for (int idx = tid; idx < total; idx += nthreads) {
             int rem = idx, w = -1;
             for (int k = k_lo; k <= k_hi; ++k) {
                 const int s = t - kGsLag * k;
-                const int h0 = L.hstart[s], cnt = L.hstart[s + 1] - h0;
+                const int h0 = hs[s], cnt = hs[s + 1] - h0;
                 if (rem < cnt) {
                     w = h0 + rem;
                     break;
                 }
                 rem -= cnt;
             }
-            gs_elem<D, LD>(L, Ti, coef + o, dinv + o, b + o, x + o, w);
+            gs_elem<D, LD, PITCH, PF>(L, rbuse, Tuse, coef + o, dinv + o, b + o, x + o, w);
         }
         // release/acquire at cluster scope; the acquire side invalidates L1 (CCTL.IVALL), so the next
         // step's plain loads of x see what the other CTAs of the cluster wrote in this one
@@ -252,8 +277,8 @@ __global__ void __launch_bounds__(kThreads) k_gs_step(LevelDev L, const double* 
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= cnt) return;
     const size_t o = (size_t)blockIdx.y * L.M * L.G;
-    gs_elem<D, LdL2>(L, T + (size_t)blockIdx.y * L.D * kTabEntries * kTabPitch, coef + o, dinv + o, b + o, x + o,
-                     h0 + j);
+    gs_elem<D, LdL2, kTabPitch>(L, L.rowbase, T + (size_t)blockIdx.y * L.D * kTabEntries * kTabPitch, coef + o, dinv + o,
+                                b + o, x + o, h0 + j);
 }
 
 static int g_num_sms = 0;
@@ -267,14 +292,32 @@ static int num_sms() {
     return g_num_sms;
 }
 
-// tuning switches (read once): PDEOP_GS_THREADS = 512 | 1024, PDEOP_GS_LD = l1 | l2
-static int g_gs_threads = 0, g_gs_l2 = -1;
+// tuning switches (read once): PDEOP_GS_SMEM = 0 | 1, PDEOP_GS_PF = 0 | 1
+static int g_gs_threads = 0, g_gs_smem = 1, g_gs_pf = 0;
 static void gs_tuning() {
     if (g_gs_threads) return;
-    const char* e = getenv("PDEOP_GS_THREADS");
-    g_gs_threads = (e && atoi(e) == 1024) ? 1024 : 512;
-    const char* l = getenv("PDEOP_GS_LD");
-    g_gs_l2 = (l && strcmp(l, "l2") == 0) ? 1 : 0;
+    g_gs_threads = 512;
+    const char* m = getenv("PDEOP_GS_SMEM");
+    g_gs_smem = (m && atoi(m) == 0) ? 0 : 1;
+    const char* f = getenv("PDEOP_GS_PF");
+    g_gs_pf = (f && atoi(f) == 1) ? 1 : 0;
+}
+
+template <int D, int THREADS, int MINB, int PS, bool PF>
+static void launch_gs_inst(cudaLaunchConfig_t& cfg, const LevelDev& L, const double* T, const double* coef,
+                           const double* dinv, const double* b, double* x, int nsweeps, const int* done) {
+    auto kern = k_gs_cluster<D, THREADS, MINB, LdPlain, PS, PF>;
+    size_t smem = 0;
+    if (PS > 0) {
+        smem = (size_t)D * kTabEntries * PS * sizeof(double) + ((size_t)(L.S + 8) * L.N[0] + 8 + L.S + 1) * sizeof(int);
+        static size_t set_for = 0;   // per instantiation
+        if (smem > set_for) {
+            note(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            set_for = smem;
+        }
+    }
+    cfg.dynamicSmemBytes = smem;
+    note(cudaLaunchKernelEx(&cfg, kern, L, T, coef, dinv, b, x, nsweeps, done));
 }
 
 template <int D>
@@ -282,6 +325,19 @@ static void launch_gs_cluster(cudaStream_t s, const LevelDev& L, int B, const do
                               const double* dinv, const double* b, double* x, int nsweeps, const int* done) {
     gs_tuning();
     const int threads = g_gs_threads;
+    const int per_sm = 1;   // CTAs per SM (register-limited: 128 regs/thread x 512 threads)
+    int maxn = L.N[0] > L.N[1] ? L.N[0] : L.N[1];
+    maxn = (maxn > L.N[2] ? maxn : L.N[2]) + 2 * kTabPad;
+    int ps = 0;
+    if (g_gs_smem) {
+        if (maxn <= 40) ps = 40;
+        else if (maxn <= 72) ps = 72;
+        else if (maxn <= 136) ps = 136;
+        else if (maxn <= 264 && D <= 2) ps = 264;
+        // index tables must fit next to the K tables
+        const size_t smem = (size_t)D * kTabEntries * ps * 8 + ((size_t)(L.S + 8) * L.N[0] + 8 + L.S + 1) * 4;
+        if (smem > (size_t)(per_sm == 2 ? 110 : 220) * 1024) ps = 0;
+    }
     // cluster size: as many CTAs per instance as fit on the chip at once, capped by the portable
     // maximum (8) and by the work of one step (largest hyperplane x sweeps in flight)
     int maxh = 0;
@@ -291,14 +347,13 @@ static void launch_gs_cluster(cudaStream_t s, const LevelDev& L, int B, const do
         maxh = maxh < c ? maxh : c;
     }
     int want = (maxh * (nsweeps < 5 ? nsweeps : 5) + threads - 1) / threads;
-    int fit = num_sms() / (B > 0 ? B : 1);
+    int fit = per_sm * num_sms() / (B > 0 ? B : 1);
     int csize = 1;
     while (csize * 2 <= 8 && csize * 2 <= fit && csize < want) csize *= 2;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(B * csize));
     cfg.blockDim = dim3(threads);
-    cfg.dynamicSmemBytes = 0;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -307,13 +362,16 @@ static void launch_gs_cluster(cudaStream_t s, const LevelDev& L, int B, const do
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (threads == 1024) {
-        if (g_gs_l2) note(cudaLaunchKernelEx(&cfg, k_gs_cluster<D, 1024, LdL2>, L, T, coef, dinv, b, x, nsweeps, done));
-        else note(cudaLaunchKernelEx(&cfg, k_gs_cluster<D, 1024, LdPlain>, L, T, coef, dinv, b, x, nsweeps, done));
-    } else {
-        if (g_gs_l2) note(cudaLaunchKernelEx(&cfg, k_gs_cluster<D, 512, LdL2>, L, T, coef, dinv, b, x, nsweeps, done));
-        else note(cudaLaunchKernelEx(&cfg, k_gs_cluster<D, 512, LdPlain>, L, T, coef, dinv, b, x, nsweeps, done));
+#define PDEOP_GS_DISPATCH(PF)                                                                           \
+    switch (ps) {                                                                                       \
+        case 40: launch_gs_inst<D, 512, 1, 40, PF>(cfg, L, T, coef, dinv, b, x, nsweeps, done); break;   \
+        case 72: launch_gs_inst<D, 512, 1, 72, PF>(cfg, L, T, coef, dinv, b, x, nsweeps, done); break;   \
+        case 136: launch_gs_inst<D, 512, 1, 136, PF>(cfg, L, T, coef, dinv, b, x, nsweeps, done); break; \
+        case 264: launch_gs_inst<D, 512, 1, 264, PF>(cfg, L, T, coef, dinv, b, x, nsweeps, done); break; \
+        default: launch_gs_inst<D, 512, 1, 0, PF>(cfg, L, T, coef, dinv, b, x, nsweeps, done); break;    \
     }
+    if (g_gs_pf) { PDEOP_GS_DISPATCH(true) } else { PDEOP_GS_DISPATCH(false) }
+#undef PDEOP_GS_DISPATCH
 }
 
 template <int D>

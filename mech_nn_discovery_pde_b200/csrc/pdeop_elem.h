@@ -144,7 +144,8 @@ PDEOP_HD int neighbor_pos(const LevelDev& L, int s, int i0, int i1, int o) {
 }
 
 // table of (instance, active axis a): entry e of line position i is Tab(T,a)[e*kTabPitch + i + kTabPad]
-PDEOP_HD const double* axis_table(const double* T, int a) { return T + (size_t)a * kTabEntries * kTabPitch; }
+template <int PITCH>
+PDEOP_HD const double* axis_table(const double* T, int a) { return T + a * (kTabEntries * PITCH); }
 
 // ------------------------------------------------------------------------------------------------
 // acc[m] = sum over OFF-POINT couplings  K[(g,m),(g',m')] x[g',m'],  g' = g + o e_a, o in [-4,4]\{0}
@@ -153,13 +154,22 @@ PDEOP_HD const double* axis_table(const double* T, int a) { return T + (size_t)a
 // because the tables are zero-padded by 4 positions on either side.  All table loads are
 // [position pointer + compile-time offset]; vector loads use one pointer per channel plane and axis.
 // ------------------------------------------------------------------------------------------------
-template <int D, class LD>
-PDEOP_HD void k_neighbors(const LevelDev& L, const double* __restrict__ T, const double* x, int i0, int i1, int i2,
-                          double acc[1 + 2 * D]) {
+// PITCH: table pitch (kTabPitch for tables in global memory, a smaller compile-time pitch for the copy the
+// Gauss-Seidel kernel stages in shared memory); rowbase: L.rowbase or its shared-memory copy.
+// keeps the compiler from sinking a batch of loads down to their first use (device only)
+#if defined(__CUDA_ARCH__)
+#define PDEOP_LOAD_FENCE() asm volatile("" ::: "memory")
+#else
+#define PDEOP_LOAD_FENCE()
+#endif
+
+template <int D, class LD, int PITCH>
+PDEOP_HD void k_neighbors(const LevelDev& L, const int* __restrict__ rowbase, const double* __restrict__ T,
+                          const double* x, int i0, int i1, int i2, double acc[1 + 2 * D]) {
     const int G = L.G, N0 = L.N[0];
     const int idx[3] = {i0, i1, i2};
     // rb[o*N0] = rowbase[s+o][i0],  rb[o*N0 + o] = rowbase[s+o][i0+o]
-    const int* __restrict__ rb = L.rowbase + (i0 + i1 + i2 + 4) * N0 + i0;
+    const int* __restrict__ rb = rowbase + (i0 + i1 + i2 + 4) * N0 + i0;
 #pragma unroll
     for (int m = 0; m < 1 + 2 * D; ++m) acc[m] = 0.0;
 #pragma unroll
@@ -167,32 +177,83 @@ PDEOP_HD void k_neighbors(const LevelDev& L, const double* __restrict__ T, const
         const int ax = 3 - D + a;
         const int n = L.N[ax];
         const int i = idx[ax];
-        const double* __restrict__ Ta = axis_table(T, a) + (i + kTabPad);
+        const double* __restrict__ Ta = axis_table<PITCH>(T, a) + (i + kTabPad);
         const double* xu = x;
         const double* xp = x + (1 + a) * G;
         const double* xq = x + (1 + D + a) * G;
-        double au = 0.0, ap = 0.0, aq = 0.0;
+        // phase 1: all 24 neighbour loads of this axis in flight together (one memory round trip per axis
+        // instead of one per neighbour: the kernels built on this body are latency-bound, not bandwidth-bound)
+        double un[8], pn[8], qn[8];
 #pragma unroll
-        for (int o = -4; o <= 4; ++o) {
-            if (o == 0) continue;
+        for (int j = 0; j < 8; ++j) {
+            const int o = j < 4 ? j - 4 : j - 3;
             const bool ok = (unsigned)(i + o) < (unsigned)n;
             int wn;
             if (ax == 2) wn = rb[o * N0] + i1;
             else if (ax == 1) wn = rb[o * N0] + i1 + o;
             else wn = rb[o * N0 + o] + i1;
-            const double un = ok ? LD::ld(xu + wn) : 0.0;
-            const double pn = ok ? LD::ld(xp + wn) : 0.0;
-            const double qn = ok ? LD::ld(xq + wn) : 0.0;
-            // explicit fma: the same bits from every kernel that inlines this body (and from the host emulator)
-            au = fma(Ta[(T_UU + o + 4) * kTabPitch], un, au);
-            au = fma(Ta[(T_UP - o + 4) * kTabPitch + o], pn, au);
-            au = fma(Ta[(T_UQ - o + 4) * kTabPitch + o], qn, au);
-            ap = fma(Ta[(T_UP + o + 4) * kTabPitch], un, ap);
-            aq = fma(Ta[(T_UQ + o + 4) * kTabPitch], un, aq);
+            un[j] = ok ? LD::ld(xu + wn) : 0.0;
+            pn[j] = ok ? LD::ld(xp + wn) : 0.0;
+            qn[j] = ok ? LD::ld(xq + wn) : 0.0;
+        }
+        PDEOP_LOAD_FENCE();
+        // phase 2: explicit fma => the same bits from every kernel that inlines this body and from the emulator
+        double au = 0.0, ap = 0.0, aq = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int o = j < 4 ? j - 4 : j - 3;
+            au = fma(Ta[(T_UU + o + 4) * PITCH], un[j], au);
+            au = fma(Ta[(T_UP - o + 4) * PITCH + o], pn[j], au);
+            au = fma(Ta[(T_UQ - o + 4) * PITCH + o], qn[j], au);
+            ap = fma(Ta[(T_UP + o + 4) * PITCH], un[j], ap);
+            aq = fma(Ta[(T_UQ + o + 4) * PITCH], un[j], aq);
         }
         acc[0] += au;
         acc[1 + a] += ap;
         acc[1 + D + a] += aq;
+    }
+}
+
+// Register-free memory parallelism: issue L1 prefetches for every vector address the point update will read
+// (neighbours of all axes + own point) before the gather starts.  No-op on the host.
+PDEOP_HD void prefetch_l1(const void* p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
+template <int D>
+PDEOP_HD void gs_prefetch(const LevelDev& L, const int* __restrict__ rowbase, const double* coef, const double* dinv,
+                          const double* b, const double* x, int w, int i0, int i1, int i2) {
+    const int G = L.G, N0 = L.N[0];
+    const int idx[3] = {i0, i1, i2};
+    const int* __restrict__ rb = rowbase + (i0 + i1 + i2 + 4) * N0 + i0;
+#pragma unroll
+    for (int m = 0; m < 1 + 2 * D; ++m) {
+        prefetch_l1(x + m * G + w);
+        prefetch_l1(b + m * G + w);
+        prefetch_l1(coef + m * G + w);
+        prefetch_l1(dinv + m * G + w);
+    }
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+        const int ax = 3 - D + a;
+        const int n = L.N[ax];
+        const int i = idx[ax];
+#pragma unroll
+        for (int o = -4; o <= 4; ++o) {
+            if (o == 0) continue;
+            if ((unsigned)(i + o) >= (unsigned)n) continue;
+            int wn;
+            if (ax == 2) wn = rb[o * N0] + i1;
+            else if (ax == 1) wn = rb[o * N0] + i1 + o;
+            else wn = rb[o * N0 + o] + i1;
+            prefetch_l1(x + wn);
+            prefetch_l1(x + (1 + a) * G + wn);
+            prefetch_l1(x + (1 + D + a) * G + wn);
+        }
     }
 }
 
@@ -206,19 +267,19 @@ struct PointLocal {
     double up[D], uq[D], pp[D], qq[D], pq[D];
 };
 
-template <int D>
+template <int D, int PITCH>
 PDEOP_HD void load_axis_local(const double* __restrict__ T, int i0, int i1, int i2, PointLocal<D>& pl) {
     const int idx[3] = {i0, i1, i2};
     pl.uu = 0.0;
 #pragma unroll
     for (int a = 0; a < D; ++a) {
-        const double* __restrict__ Ta = axis_table(T, a) + (idx[3 - D + a] + kTabPad);
-        pl.uu += Ta[(T_UU + 4) * kTabPitch];
-        pl.up[a] = Ta[(T_UP + 4) * kTabPitch];
-        pl.uq[a] = Ta[(T_UQ + 4) * kTabPitch];
-        pl.pp[a] = Ta[T_PP * kTabPitch];
-        pl.qq[a] = Ta[T_QQ * kTabPitch];
-        pl.pq[a] = Ta[T_PQ * kTabPitch];
+        const double* __restrict__ Ta = axis_table<PITCH>(T, a) + (idx[3 - D + a] + kTabPad);
+        pl.uu += Ta[(T_UU + 4) * PITCH];
+        pl.up[a] = Ta[(T_UP + 4) * PITCH];
+        pl.uq[a] = Ta[(T_UQ + 4) * PITCH];
+        pl.pp[a] = Ta[T_PP * PITCH];
+        pl.qq[a] = Ta[T_QQ * PITCH];
+        pl.pq[a] = Ta[T_PQ * PITCH];
     }
 }
 
@@ -232,7 +293,7 @@ PDEOP_HD void load_local(const LevelDev& L, const double* __restrict__ T, const 
         pl.c[m] = eq ? coef[m * G + w] : 0.0;
         pl.ini[m] = (double)((flags >> (4 + 2 * m)) & 3);
     }
-    load_axis_local<D>(T, i0, i1, i2, pl);
+    load_axis_local<D, kTabPitch>(T, i0, i1, i2, pl);
 }
 
 // diagonal of K at channel m of a point
@@ -268,7 +329,7 @@ PDEOP_HD void apply_k_elem(const LevelDev& L, const double* __restrict__ T, cons
     unpack_coord(L.coord[w], i0, i1, i2);
     const int flags = L.flags[w];
     double acc[M];
-    k_neighbors<D, LdPlain>(L, T, x, i0, i1, i2, acc);
+    k_neighbors<D, LdPlain, kTabPitch>(L, L.rowbase, T, x, i0, i1, i2, acc);
     PointLocal<D> pl;
     load_local<D>(L, T, coef, w, i0, i1, i2, flags, pl);
     double xl[M];
@@ -299,25 +360,34 @@ PDEOP_HD void apply_k_elem(const LevelDev& L, const double* __restrict__ T, cons
 //   x_j <- (b_j - sum_{k != j} K_jk x_k) / K_jj   with already-updated values for k < j.
 // The equation-row part of the point block is rank one (c c^T): the running sum S = c.x is kept up to
 // date as channels are updated, and the division is a multiplication by the precomputed reciprocal diagonal.
-template <int D, class LD>
-PDEOP_HD void gs_elem(const LevelDev& L, const double* __restrict__ T, const double* __restrict__ coef,
-                      const double* __restrict__ dinv, const double* __restrict__ b, double* x, int w) {
+template <int D, class LD, int PITCH, bool PF = false>
+PDEOP_HD void gs_elem(const LevelDev& L, const int* __restrict__ rowbase, const double* __restrict__ T,
+                      const double* __restrict__ coef, const double* __restrict__ dinv,
+                      const double* __restrict__ b, double* x, int w) {
     constexpr int M = 1 + 2 * D;
     const int G = L.G;
     int i0, i1, i2;
     unpack_coord(L.coord[w], i0, i1, i2);
+    if (PF) gs_prefetch<D>(L, rowbase, coef, dinv, b, x, w, i0, i1, i2);
     const bool eq = L.flags[w] & 1;
-    double acc[M];
-    k_neighbors<D, LD>(L, T, x, i0, i1, i2, acc);
-    PointLocal<D> pl;
-    load_axis_local<D>(T, i0, i1, i2, pl);
-    double xl[M], c[M];
-    double S = 0.0;
+    // own-point loads first: their latency overlaps the neighbour gathers
+    double xl[M], c[M], bl[M], di[M];
 #pragma unroll
     for (int m = 0; m < M; ++m) {
         xl[m] = LD::ld(x + m * G + w);
         c[m] = eq ? coef[m * G + w] : 0.0;
-        acc[m] = b[m * G + w] - acc[m];
+        bl[m] = b[m * G + w];
+        di[m] = dinv[m * G + w];
+    }
+    PDEOP_LOAD_FENCE();
+    double acc[M];
+    k_neighbors<D, LD, PITCH>(L, rowbase, T, x, i0, i1, i2, acc);
+    PointLocal<D> pl;
+    load_axis_local<D, PITCH>(T, i0, i1, i2, pl);
+    double S = 0.0;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        acc[m] = bl[m] - acc[m];
         S = fma(c[m], xl[m], S);
     }
 #pragma unroll
@@ -339,7 +409,7 @@ PDEOP_HD void gs_elem(const LevelDev& L, const double* __restrict__ T, const dou
             off = fma(pl.uq[a], xl[0], off);
             off = fma(pl.pq[a], xl[1 + a], off);
         }
-        const double xn = (acc[m] - off) * dinv[m * G + w];
+        const double xn = (acc[m] - off) * di[m];
         S = fma(c[m], xn, t);
         xl[m] = xn;
     }
@@ -457,7 +527,7 @@ PDEOP_HD void dense_elem(const LevelDev& L, const double* __restrict__ T, const 
         const int ax = 3 - D + a;
         const int nn = L.N[ax];
         const int i = idx[ax];
-        const double* Ta = axis_table(T, a) + (i + kTabPad);
+        const double* Ta = axis_table<kTabPitch>(T, a) + (i + kTabPad);
         const size_t ru = r0, rp = r0 + 1 + a, rq = r0 + 1 + D + a;
         for (int o = -4; o <= 4; ++o) {
             if (o == 0) continue;

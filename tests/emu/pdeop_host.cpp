@@ -100,8 +100,8 @@ static void gs_t(const LevelDev& L, int B, const double* T, const double* coef, 
                 const int s = t - kGsLag * k;
                 if (s < 0 || s >= L.S) continue;
                 for (int w = hs[s]; w < hs[s + 1]; ++w)
-                    gs_elem<D, LdPlain>(L, T + ib * tstride(L), coef + ib * vstride(L), dinv + ib * vstride(L),
-                                        b + ib * vstride(L), x + ib * vstride(L), w);
+                    gs_elem<D, LdPlain, kTabPitch>(L, L.rowbase, T + ib * tstride(L), coef + ib * vstride(L),
+                                                   dinv + ib * vstride(L), b + ib * vstride(L), x + ib * vstride(L), w);
             }
 }
 
