@@ -5,7 +5,7 @@
 
 A "step" is one forward+backward of the multigrid PDE layer over one batch of synthetic instances
 (SURVEY.md section 8(d) inputs).  Default workload: Ginzburg-Landau 32x64x64 space-time grid, 32 instances
-per GPU, n_grid=3, downsample_first=True, fp64, config.py default knobs.  One process per GPU; the batch
+per GPU, n_grid=4, downsample_first=False (as in the reference's GL script), fp64, config.py default knobs.  One process per GPU; the batch
 is sharded (weak scaling: 32 instances per GPU) with no communication inside the solve; the only
 collective is the all-reduce of the learned-parameter gradient.
 
@@ -160,11 +160,15 @@ def algorithmic_bytes(plan, cfgs, B):
     M = plan.M
     G0 = plan.G
     nc = plan.lib.query(plan.handle, _lib.Q_G, plan.n_grid - 1) * M
+    # coarsest level in band ordering (longest axis outermost): half-bandwidth 4*inner*M + M - 1
+    cd = plan.dims_list[-1]
+    inner = int(np.prod(cd)) // max(cd)
+    bw = min(4 * inner * M + M - 1, nc - 1)
     nsw = cfgs["gs_pre"]
     return {
         "gs_fine": 4 * M * w * G0 * B * nsw,               # per sweep: read x, b, coeffs; write x
         "apply_fine": 3 * M * w * G0 * B,                   # read z, coeffs; write y  (residual: +b)
-        "coarse_solve": 2 * (nc * (nc + 1) // 2) * w * B,   # L read once per triangular solve
+        "coarse_solve": 2 * nc * (bw + 1) * w * B,          # band of L streamed once per triangular solve
     }
 
 

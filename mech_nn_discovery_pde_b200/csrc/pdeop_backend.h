@@ -44,7 +44,8 @@ void be_dinv(stream_t st, const LevelDev& L, int B, const double* T, const doubl
 void be_dense(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, double* Kd);
 // in-place lower Cholesky of B dense n x n matrices; state->chol_info set on a non-positive pivot
 // (bw = half-bandwidth of the matrix in the dense ordering; nothing outside the band is touched)
-// Linv: B * ceil(n/kSolveBlk) * kSolveBlk^2 doubles receiving the inverses of the diagonal blocks of L
+// Linv: 2 * B * ceil(n/kSolveBlk) * kSolveBlk^2 doubles receiving the inverses of the diagonal blocks of L and,
+// after them, their transposes
 void be_cholesky(stream_t st, int B, int n, int bw, double* Kd, double* Linv, FgmresState* state);
 // out = (L L^T)^-1 rhs for the dense system of level L (n = M*G); rhs/out in wave/planar layout, the
 // factor in band ordering; work: 2*B*n doubles

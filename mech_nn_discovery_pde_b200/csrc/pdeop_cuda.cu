@@ -860,6 +860,10 @@ __global__ void __launch_bounds__(kSolveBlk) k_trtri(int n, const double* __rest
         }
         Ib[(size_t)i * kSolveBlk + j] = v;
     }
+    // transpose copy (upper triangular), used by the backward solve with the same warp-per-row kernel
+    __syncthreads();
+    double* It = Linv + ((size_t)gridDim.y * nblk + (size_t)ib * nblk + kb) * kSolveBlk * kSolveBlk;
+    for (int i = 0; i < kSolveBlk; ++i) It[(size_t)j * kSolveBlk + i] = Ib[(size_t)i * kSolveBlk + j];
 }
 
 void be_cholesky(stream_t st, int B, int n, int bw, double* Kd, double* Linv, FgmresState* state) {
@@ -919,9 +923,9 @@ __global__ void __launch_bounds__(256) k_fwd_gemv(int n, const double* __restric
     if (lane == 0) t[(size_t)ib * n + k0 + row] = r[(size_t)ib * n + k0 + row] - a;
 }
 
-// y_k = Linv_kk t_k  (lower triangular block): one warp per row
+// y_k = M_kk t_k for a triangular kSolveBlk block (upper=0: lower triangular, upper=1: upper): one warp per row
 __global__ void __launch_bounds__(256) k_blk_mv(int n, const double* __restrict__ Linv, int nblk, int kb, int w,
-                                                const double* t, double* y, const int* done) {
+                                                const double* t, double* y, int upper, const int* done) {
     if (done && *done) return;
     __shared__ double ts[kSolveBlk];
     const int ib = blockIdx.y;
@@ -933,36 +937,16 @@ __global__ void __launch_bounds__(256) k_blk_mv(int n, const double* __restrict_
     const int lane = threadIdx.x & 31;
     const double* Ir = Linv + ((size_t)ib * nblk + kb) * kSolveBlk * kSolveBlk + (size_t)row * kSolveBlk;
     double a = 0.0;
-    for (int c = lane; c <= row; c += 32) a += Ir[c] * ts[c];
+    const int c0 = upper ? (row & ~31) : 0, c1 = upper ? w : row + 1;
+    for (int c = c0 + lane; c < c1; c += 32)
+        if (!upper || c >= row) a += Ir[c] * ts[c];
     a = warp_sum(a);
     if (lane == 0) y[(size_t)ib * n + k0 + row] = a;
 }
 
-// z_k = Linv_kk^T y_k : one thread per output i (coalesced along the rows of Linv); result goes to zout
-__global__ void __launch_bounds__(kSolveBlk) k_blk_mv_t(int n, const double* __restrict__ Linv, int nblk, int kb,
-                                                       int w, const double* y, double* zout, const int* done) {
-    if (done && *done) return;
-    __shared__ double ys[kSolveBlk];
-    const int ib = blockIdx.x;
-    const int k0 = kb * kSolveBlk;
-    const int i = threadIdx.x;
-    if (i < w) ys[i] = y[(size_t)ib * n + k0 + i];
-    __syncthreads();
-    if (i >= w) return;
-    const double* Ib = Linv + ((size_t)ib * nblk + kb) * kSolveBlk * kSolveBlk + i;
-    double a0 = 0.0, a1 = 0.0;
-    int r = i;
-    for (; r + 1 < w; r += 2) {
-        a0 += Ib[(size_t)r * kSolveBlk] * ys[r];
-        a1 += Ib[(size_t)(r + 1) * kSolveBlk] * ys[r + 1];
-    }
-    if (r < w) a0 += Ib[(size_t)r * kSolveBlk] * ys[r];
-    zout[(size_t)ib * n + k0 + i] = a0 + a1;
-}
-
 // y[c] -= sum_{r in [k0,k0+w)} L[r][c] z[r]  for c in [c_lo,k0) (one thread per column, coalesced along the rows
 // of L), and y[k0+i] = z[i] for the block itself; z = zsrc[k0..k0+w)
-__global__ void __launch_bounds__(256) k_bwd_update(int n, const double* __restrict__ Lf, size_t strideL, int k0,
+__global__ void __launch_bounds__(128) k_bwd_update(int n, const double* __restrict__ Lf, size_t strideL, int k0,
                                                     int w, int c_lo, const double* __restrict__ zsrc, double* y,
                                                     const int* done) {
     if (done && *done) return;
@@ -978,16 +962,19 @@ __global__ void __launch_bounds__(256) k_bwd_update(int n, const double* __restr
         return;
     }
     const double* Lc = Lf + (size_t)ib * strideL + (size_t)k0 * n + c;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    double acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.0;
     int r = 0;
-    for (; r + 3 < w; r += 4) {
-        a0 += Lc[(size_t)r * n] * zs[r];
-        a1 += Lc[(size_t)(r + 1) * n] * zs[r + 1];
-        a2 += Lc[(size_t)(r + 2) * n] * zs[r + 2];
-        a3 += Lc[(size_t)(r + 3) * n] * zs[r + 3];
+    for (; r + 7 < w; r += 8) {
+        double l[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) l[q] = Lc[(size_t)(r + q) * n];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] += l[q] * zs[r + q];
     }
-    for (; r < w; ++r) a0 += Lc[(size_t)r * n] * zs[r];
-    yb[c] -= (a0 + a1) + (a2 + a3);
+    for (; r < w; ++r) acc[0] += Lc[(size_t)r * n] * zs[r];
+    yb[c] -= ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
 }
 
 __global__ void __launch_bounds__(kThreads) k_to_band(LevelDev L, const double* __restrict__ wave,
@@ -1014,6 +1001,7 @@ void be_chol_solve(stream_t st, const LevelDev& L, int B, const double* Lf, cons
     const int bw = L.bw;
     const size_t strideL = (size_t)n * n;
     const int nblk = (n + kSolveBlk - 1) / kSolveBlk;
+    const double* LinvT = Linv + (size_t)B * nblk * kSolveBlk * kSolveBlk;   // transposed inverse blocks
     double* rb = work;                  // right-hand side in band ordering; reused as block temporary
     double* y = work + (size_t)B * n;   // solution in band ordering
     k_to_band<<<dim3(cdiv(L.G, kThreads), B), kThreads, 0, s>>>(L, rhs, rb, done);
@@ -1029,7 +1017,7 @@ void be_chol_solve(stream_t st, const LevelDev& L, int B, const double* Lf, cons
             k_fwd_gemv<<<dim3(cdiv(w, 8), B), 256, 0, s>>>(n, Lf, strideL, k0, w, c_lo, rb, y, rb, done);
             PDEOP_COUNT(1);
         }
-        k_blk_mv<<<dim3(cdiv(w, 8), B), 256, 0, s>>>(n, Linv, nblk, kb, w, rb, y, done);
+        k_blk_mv<<<dim3(cdiv(w, 8), B), 256, 0, s>>>(n, Linv, nblk, kb, w, rb, y, 0, done);
         PDEOP_COUNT(1);
     }
     // backward: y <- L^-T y.  Per block row (descending): z_k = Linv_kk^T y_k (into rb), then the update kernel
@@ -1037,12 +1025,12 @@ void be_chol_solve(stream_t st, const LevelDev& L, int B, const double* Lf, cons
     for (int kb = nblk - 1; kb >= 0; --kb) {
         const int k0 = kb * kSolveBlk;
         const int w = k0 + kSolveBlk < n ? kSolveBlk : n - k0;
-        k_blk_mv_t<<<B, kSolveBlk, 0, s>>>(n, Linv, nblk, kb, w, y, rb, done);
+        k_blk_mv<<<dim3(cdiv(w, 8), B), 256, 0, s>>>(n, LinvT, nblk, kb, w, y, rb, 1, done);
         PDEOP_COUNT(1);
         int c_lo = k0 - bw;
         if (c_lo < 0) c_lo = 0;
         c_lo &= ~31;
-        k_bwd_update<<<dim3(cdiv(k0 - c_lo + w, 256), B), 256, 0, s>>>(n, Lf, strideL, k0, w, c_lo, rb, y, done);
+        k_bwd_update<<<dim3(cdiv(k0 - c_lo + w, 128), B), 128, 0, s>>>(n, Lf, strideL, k0, w, c_lo, rb, y, done);
         PDEOP_COUNT(1);
     }
     k_from_band<<<dim3(cdiv(L.G, kThreads), B), kThreads, 0, s>>>(L, y, out, done);

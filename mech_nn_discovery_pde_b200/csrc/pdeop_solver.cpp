@@ -238,7 +238,7 @@ extern "C" int pdeop_plan_create(int d, const int* dims, int order, int batch, i
     pl->off_Kd = poff;
     poff += (size_t)batch * pl->nc * pl->nc;
     pl->off_Linv = poff;
-    poff += (size_t)batch * ((pl->nc + kSolveBlk - 1) / kSolveBlk) * kSolveBlk * kSolveBlk;
+    poff += 2 * (size_t)batch * ((pl->nc + kSolveBlk - 1) / kSolveBlk) * kSolveBlk * kSolveBlk;  // inverse + transpose
     pl->persist_doubles = poff;
     *out = pl;
     return 0;
