@@ -64,3 +64,50 @@ def test_layer_vs_reference(name):
         assert int(out["info_fwd"][0]) == int(info[0, 0]) and int(out["info_bwd"][0]) == int(info[1, 0])
         assert abs(out["info_fwd"][1] - info[0, 1]) <= 1e-6 * info[0, 1]
         assert abs(out["info_bwd"][1] - info[1, 1]) <= 1e-6 * info[1, 1]
+
+
+def test_1d_multigrid_vs_oracle():
+    """1-D grids go through the same kernels (D=1 template); no golden from the reference scripts, so the
+    oracle (pinned on 2-D/3-D goldens and 1-D dense goldens) is the checker."""
+    import torch
+    from mech_nn_discovery_pde_b200 import MultigridLayer
+    from oracle import pde_oracle as O
+    from oracle.cases import make_inputs
+    lib = emu_library()
+    dims, B, n_grid = (32,), 2, 2
+    iv = IV_LISTS["kamani"]
+    st = O.build_structure(dims, iv)
+    inp = make_inputs(dims, B, st.n_init, seed=5)
+    g_out = inp["loss_w"].reshape(B, -1)
+    ref = O.mg_layer(dims, iv, inp["coeffs"], inp["rhs"], inp["iv_rhs"], inp["steps"], n_grid, True, grad_out=g_out)
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64)
+    layer = MultigridLayer(bs=B, coord_dims=dims, order=2, n_ind_dim=1, n_iv=1, n_grid=n_grid, downsample_first=True,
+                           init_index_mi_list=iv, n_iv_steps=1, _library=lib)
+    coeffs = t(inp["coeffs"]).requires_grad_(True)
+    rhs = t(inp["rhs"]).requires_grad_(True)
+    ivr = t(inp["iv_rhs"]).requires_grad_(True)
+    steps = [t(s).requires_grad_(True) for s in inp["steps"]]
+    u0, u, _ = layer(coeffs, rhs, ivr, list(steps))
+    (u * t(inp["loss_w"]).reshape(u.shape)).sum().backward()
+    assert rel(u.detach().numpy().reshape(B, -1), ref.x) < 1e-8
+    assert rel(coeffs.grad.numpy(), ref.d_coeffs) < 1e-8
+    assert rel(rhs.grad.numpy(), ref.d_rhs) < 1e-8
+    assert rel(steps[0].grad.numpy(), ref.d_steps[0]) < 1e-7
+
+
+def test_rhs_grad_fp32_quirk_and_knobs():
+    """PDEConfig knobs are read at call time; the fp32 add_pad quirk of the reference is reproducible on request."""
+    from mech_nn_discovery_pde_b200.config import PDEConfig
+
+    class Cfg(PDEConfig):
+        rhs_grad_fp32_quirk = True
+    lib = emu_library()
+    z, out = run_layer_case(lib, "cpu", "mg_2d_16x16_g2", config=Cfg)
+    assert np.array_equal(out["d_rhs"], out["d_rhs"].astype(np.float32).astype(np.float64))
+    assert rel(out["d_rhs"], z["d_rhs_fp32quirk"]) < 1e-7
+
+    class Short(PDEConfig):
+        mg_fgmres_max_iter_forward = 20
+        mg_fgmres_max_iter_backward = 10
+    z, out = run_layer_case(lib, "cpu", "mg_2d_16x16_g2", config=Short)
+    assert int(out["info_fwd"][0]) == 20 and int(out["info_bwd"][0]) == 10
