@@ -944,37 +944,64 @@ __global__ void __launch_bounds__(256) k_blk_mv(int n, const double* __restrict_
     if (lane == 0) y[(size_t)ib * n + k0 + row] = a;
 }
 
-// y[c] -= sum_{r in [k0,k0+w)} L[r][c] z[r]  for c in [c_lo,k0) (one thread per column, coalesced along the rows
-// of L), and y[k0+i] = z[i] for the block itself; z = zsrc[k0..k0+w)
-__global__ void __launch_bounds__(128) k_bwd_update(int n, const double* __restrict__ Lf, size_t strideL, int k0,
-                                                    int w, int c_lo, const double* __restrict__ zsrc, double* y,
-                                                    const int* done) {
+// y[c] -= sum_{r in [k0,k0+w)} L[r][c] z[r]  for c in [c_lo,k0), and y[k0+i] = z[i] for the block itself;
+// z = zsrc[k0..k0+w).  A CTA owns a tile of 128 columns; its 8 warps take the rows r = warp (mod 8) and read
+// 4 x 256 B = 1 KB contiguous per row (DRAM-page friendly, like the forward GEMV); the 8 partial sums per column
+// are combined through shared memory in a fixed order.
+constexpr int kUpdCols = 128;
+__global__ void __launch_bounds__(256) k_bwd_update(int n, const double* __restrict__ Lf, size_t strideL, int k0,
+                                                    int w, int c_lo, int c_min, const double* __restrict__ zsrc,
+                                                    double* y, const int* done) {
     if (done && *done) return;
     __shared__ double zs[kSolveBlk];
+    __shared__ double part[8][kUpdCols];
     const int ib = blockIdx.y;
     double* yb = y + (size_t)ib * n;
     for (int i = threadIdx.x; i < w; i += blockDim.x) zs[i] = zsrc[(size_t)ib * n + k0 + i];
     __syncthreads();
-    const int c = c_lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= k0 + w) return;
-    if (c >= k0) {
-        yb[c] = zs[c - k0];
+    const int cbase = c_lo + blockIdx.x * kUpdCols;
+    if (cbase >= k0) {   // tiles past the band columns copy the solved block into y
+        const int i = (cbase - k0) + threadIdx.x;
+        if (threadIdx.x < kUpdCols && i < w) yb[k0 + i] = zs[i];
         return;
     }
-    const double* Lc = Lf + (size_t)ib * strideL + (size_t)k0 * n + c;
-    double acc[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double* Lc = Lf + (size_t)ib * strideL + (size_t)k0 * n + cbase + lane;
+    bool ok[4];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) acc[q] = 0.0;
-    int r = 0;
-    for (; r + 7 < w; r += 8) {
-        double l[8];
+    for (int q = 0; q < 4; ++q) ok[q] = cbase + lane + 32 * q < k0 && cbase + lane + 32 * q >= c_min;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    int r = warp;
+    for (; r + 24 < w; r += 32) {   // 4 rows x 4 segments = 16 independent loads in flight per lane
+        double l[4][4];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) l[q] = Lc[(size_t)(r + q) * n];
+        for (int v = 0; v < 4; ++v)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) acc[q] += l[q] * zs[r + q];
+            for (int q = 0; q < 4; ++q) l[v][q] = ok[q] ? Lc[(size_t)(r + 8 * v) * n + 32 * q] : 0.0;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const double zv = zs[r + 8 * v];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] += l[v][q] * zv;
+        }
     }
-    for (; r < w; ++r) acc[0] += Lc[(size_t)r * n] * zs[r];
-    yb[c] -= ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+    for (; r < w; r += 8) {
+        const double z0 = zs[r];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] += (ok[q] ? Lc[(size_t)r * n + 32 * q] : 0.0) * z0;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) part[warp][lane + 32 * q] = acc[q];
+    __syncthreads();
+    if (threadIdx.x < kUpdCols) {
+        const int c = cbase + threadIdx.x;
+        if (c < k0 && c >= c_min) {
+            double sum = 0.0;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) sum += part[v][threadIdx.x];
+            yb[c] -= sum;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kThreads) k_to_band(LevelDev L, const double* __restrict__ wave,
@@ -1030,7 +1057,10 @@ void be_chol_solve(stream_t st, const LevelDev& L, int B, const double* Lf, cons
         int c_lo = k0 - bw;
         if (c_lo < 0) c_lo = 0;
         c_lo &= ~31;
-        k_bwd_update<<<dim3(cdiv(k0 - c_lo + w, 128), B), 128, 0, s>>>(n, Lf, strideL, k0, w, c_lo, rb, y, done);
+        // column tiles over the band columns [c_lo,k0) (rounded up to whole tiles) plus tiles copying the block
+        const int band_tiles = (int)cdiv(k0 - c_lo, kUpdCols);
+        k_bwd_update<<<dim3(band_tiles + cdiv(w, kUpdCols), B), 256, 0, s>>>(n, Lf, strideL, k0, w,
+                                                                            k0 - band_tiles * kUpdCols, c_lo, rb, y, done);
         PDEOP_COUNT(1);
     }
     k_from_band<<<dim3(cdiv(L.G, kThreads), B), kThreads, 0, s>>>(L, y, out, done);
