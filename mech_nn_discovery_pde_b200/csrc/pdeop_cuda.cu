@@ -787,55 +787,86 @@ __global__ void __launch_bounds__(128) k_chol_trsm(int n, double* A, size_t stri
 }
 
 // C[i][j] -= sum_{t in [p0,p1)} A[i][t] A[j][t]   for i in [r0,r1), j in [c0,c1), i >= j
-__global__ void __launch_bounds__(256) k_syrk(int n, double* A, size_t strideA, int r0, int r1, int c0, int c1, int p0,
-                                              int p1) {
-    const int i0 = r0 + blockIdx.x * 64, j0 = c0 + blockIdx.y * 64;
-    if (i0 + 63 < j0) return;
-    __shared__ double As[16][64 + 2], Bs[16][64 + 2];
+// fp64 has no tcgen05 kind and DMMA's rate equals the FMA pipe's on B200, so this is a register-tiled DFMA
+// kernel: 128x128 tile per CTA, 8x8 accumulators per thread (4 FMAs per shared-memory load, the ratio the
+// 128 B/clk shared-memory pipe needs to keep 64 DFMA/clk busy), next K-chunk prefetched into registers
+// while the current one is multiplied.
+constexpr int kSyrkT = 128;
+constexpr int kSyrkK = 16;
+__global__ void __launch_bounds__(256, 1) k_syrk(int n, double* A, size_t strideA, int r0, int r1, int c0, int c1,
+                                                 int p0, int p1) {
+    const int i0 = r0 + blockIdx.x * kSyrkT, j0 = c0 + blockIdx.y * kSyrkT;
+    if (i0 + kSyrkT - 1 < j0) return;   // tile entirely above the diagonal
+    __shared__ __align__(16) double As[kSyrkK][kSyrkT];
+    __shared__ __align__(16) double Bs[kSyrkK][kSyrkT];
     double* Ab = A + (size_t)blockIdx.z * strideA;
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
-    const int lrow = tid >> 2, lk = (tid & 3) * 4;
-    double acc[4][4];
+    const int lr = tid >> 1, lk = (tid & 1) * 8;   // loader: row lr of the tile, 8 consecutive k
+    const bool arow = i0 + lr < r1, brow = j0 + lr < c1;
+    const double* ap = Ab + (size_t)(i0 + lr) * n + lk;
+    const double* bp = Ab + (size_t)(j0 + lr) * n + lk;
+    double acc[8][8];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 8; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-    for (int kk = p0; kk < p1; kk += 16) {
+        for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
+    double ra[8], rb[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int k = kk + lk + q;
-            const int ia = i0 + lrow, jb = j0 + lrow;
-            As[lk + q][lrow] = (ia < r1 && k < p1) ? Ab[(size_t)ia * n + k] : 0.0;
-            Bs[lk + q][lrow] = (jb < c1 && k < p1) ? Ab[(size_t)jb * n + k] : 0.0;
+    for (int q = 0; q < 8; ++q) {
+        const int k = p0 + lk + q;
+        ra[q] = (arow && k < p1) ? ap[p0 + q] : 0.0;
+        rb[q] = (brow && k < p1) ? bp[p0 + q] : 0.0;
+    }
+    for (int kk = p0; kk < p1; kk += kSyrkK) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            As[lk + q][lr] = ra[q];
+            Bs[lk + q][lr] = rb[q];
         }
         __syncthreads();
+        if (kk + kSyrkK < p1) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            double av[4], bv[4];
+            for (int q = 0; q < 8; ++q) {
+                const int k = kk + kSyrkK + lk + q;
+                ra[q] = (arow && k < p1) ? ap[kk + kSyrkK + q] : 0.0;
+                rb[q] = (brow && k < p1) ? bp[kk + kSyrkK + q] : 0.0;
+            }
+        }
 #pragma unroll
-            for (int a = 0; a < 4; ++a) av[a] = As[k][ty * 4 + a];
+        for (int k = 0; k < kSyrkK; ++k) {
+            double av[8], bv[8];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) bv[b] = Bs[k][tx * 4 + b];
+            for (int q = 0; q < 4; ++q) {
+                const double2 a2 = *reinterpret_cast<const double2*>(&As[k][ty * 2 + 32 * q]);
+                const double2 b2 = *reinterpret_cast<const double2*>(&Bs[k][tx * 2 + 32 * q]);
+                av[2 * q] = a2.x;
+                av[2 * q + 1] = a2.y;
+                bv[2 * q] = b2.x;
+                bv[2 * q + 1] = b2.y;
+            }
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < 8; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] += av[a] * bv[b];
+                for (int b = 0; b < 8; ++b) acc[a][b] += av[a] * bv[b];
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 8; ++a) {
+        const int i = i0 + ty * 2 + (a & 1) + 32 * (a >> 1);
+        if (i >= r1) continue;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int i = i0 + ty * 4 + a, j = j0 + tx * 4 + b;
-            if (i < r1 && j < c1 && i >= j) Ab[(size_t)i * n + j] -= acc[a][b];
+        for (int b = 0; b < 8; ++b) {
+            const int j = j0 + tx * 2 + (b & 1) + 32 * (b >> 1);
+            if (j < c1 && i >= j) Ab[(size_t)i * n + j] -= acc[a][b];
         }
+    }
 }
 
 static void launch_syrk(cudaStream_t s, int B, int n, double* A, int r0, int r1, int c0, int c1, int p0, int p1) {
     if (r0 >= r1 || c0 >= c1 || p0 >= p1) return;
-    dim3 grid(cdiv(r1 - r0, 64), cdiv(c1 - c0, 64), B);
+    dim3 grid(cdiv(r1 - r0, kSyrkT), cdiv(c1 - c0, kSyrkT), B);
     k_syrk<<<grid, 256, 0, s>>>(n, A, (size_t)n * n, r0, r1, c0, c1, p0, p1);
     PDEOP_COUNT(1);
 }
