@@ -290,8 +290,15 @@ def run_ours(args, wl):
             breakdown[k]["frac_of_hbm_peak"] = ab[k] / avg_s / 1e9 / hbm_peak
     hbm_kernels = [k for k in ("gs_fine", "coarse_solve", "apply_fine") if k in breakdown]
     dom = max(hbm_kernels, key=lambda k: breakdown[k]["ms_per_step"])
+    traffic = None
+    try:   # DRAM bytes per launch of this kernel from the committed ncu --set full capture (profiles/)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if dom in tj and args.workload == "gl32" and B == wl["batch"]:
+            traffic = tj[dom]["bytes"]
+    except Exception:
+        pass
     roofline = {"kernel": dom, "bound": "hbm", "achieved": breakdown[dom]["algorithmic_gbs"], "peak": hbm_peak,
-                "unit": "GB/s", "frac": breakdown[dom]["frac_of_hbm_peak"], "traffic": None,
+                "unit": "GB/s", "frac": breakdown[dom]["frac_of_hbm_peak"], "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": ab[dom],
                 "avg_launch_ms": prof[dom][0] / prof[dom][1], "share_of_step": breakdown[dom]["share"]}
     cpu = None
