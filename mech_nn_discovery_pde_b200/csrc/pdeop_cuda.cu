@@ -194,7 +194,7 @@ void be_apply_k(stream_t st, const LevelDev& L, int B, const double* T, const do
 // together with the level's rowbase/hstart index tables: the cluster barrier invalidates L1 every step, so
 // anything read from global memory is re-fetched from L2 each step, while shared memory stays put.
 // PS == 0: tables too large for shared memory, read from global memory.
-template <int D, int THREADS, int MINB, class LD, int PS, bool PF>
+template <int D, int THREADS, int MINB, class LD, int PS>
 __global__ void __launch_bounds__(THREADS, MINB) k_gs_cluster(LevelDev L, const double* __restrict__ T,
                                                               const double* __restrict__ coef,
                                                               const double* __restrict__ dinv,
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gs_cluster(LevelDev L, const 
                 }
                 rem -= cnt;
             }
-            gs_elem<D, LD, PITCH, PF>(L, rbuse, Tuse, coef + o, dinv + o, b + o, x + o, w);
+            gs_elem<D, LD, PITCH>(L, rbuse, Tuse, coef + o, dinv + o, b + o, x + o, w);
         }
         // release/acquire at cluster scope; the acquire side invalidates L1 (CCTL.IVALL), so the next
         // step's plain loads of x see what the other CTAs of the cluster wrote in this one
@@ -292,21 +292,19 @@ static int num_sms() {
     return g_num_sms;
 }
 
-// tuning switches (read once): PDEOP_GS_SMEM = 0 | 1, PDEOP_GS_PF = 0 | 1
-static int g_gs_threads = 0, g_gs_smem = 1, g_gs_pf = 0;
+// tuning switch (read once): PDEOP_GS_SMEM = 0 disables the shared-memory staging of the tables (A/B testing)
+static int g_gs_threads = 0, g_gs_smem = 1;
 static void gs_tuning() {
     if (g_gs_threads) return;
-    g_gs_threads = 512;
+    g_gs_threads = 512;   // 128 registers/thread; 256/384/1024-thread variants were measured and are not faster
     const char* m = getenv("PDEOP_GS_SMEM");
     g_gs_smem = (m && atoi(m) == 0) ? 0 : 1;
-    const char* f = getenv("PDEOP_GS_PF");
-    g_gs_pf = (f && atoi(f) == 1) ? 1 : 0;
 }
 
-template <int D, int THREADS, int MINB, int PS, bool PF>
+template <int D, int THREADS, int MINB, int PS>
 static void launch_gs_inst(cudaLaunchConfig_t& cfg, const LevelDev& L, const double* T, const double* coef,
                            const double* dinv, const double* b, double* x, int nsweeps, const int* done) {
-    auto kern = k_gs_cluster<D, THREADS, MINB, LdPlain, PS, PF>;
+    auto kern = k_gs_cluster<D, THREADS, MINB, LdPlain, PS>;
     size_t smem = 0;
     if (PS > 0) {
         smem = (size_t)D * kTabEntries * PS * sizeof(double) + ((size_t)(L.S + 8) * L.N[0] + 8 + L.S + 1) * sizeof(int);
@@ -362,16 +360,13 @@ static void launch_gs_cluster(cudaStream_t s, const LevelDev& L, int B, const do
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-#define PDEOP_GS_DISPATCH(PF)                                                                           \
-    switch (ps) {                                                                                       \
-        case 40: launch_gs_inst<D, 512, 1, 40, PF>(cfg, L, T, coef, dinv, b, x, nsweeps, done); break;   \
-        case 72: launch_gs_inst<D, 512, 1, 72, PF>(cfg, L, T, coef, dinv, b, x, nsweeps, done); break;   \
-        case 136: launch_gs_inst<D, 512, 1, 136, PF>(cfg, L, T, coef, dinv, b, x, nsweeps, done); break; \
-        case 264: launch_gs_inst<D, 512, 1, 264, PF>(cfg, L, T, coef, dinv, b, x, nsweeps, done); break; \
-        default: launch_gs_inst<D, 512, 1, 0, PF>(cfg, L, T, coef, dinv, b, x, nsweeps, done); break;    \
+    switch (ps) {
+        case 40: launch_gs_inst<D, 512, 1, 40>(cfg, L, T, coef, dinv, b, x, nsweeps, done); break;
+        case 72: launch_gs_inst<D, 512, 1, 72>(cfg, L, T, coef, dinv, b, x, nsweeps, done); break;
+        case 136: launch_gs_inst<D, 512, 1, 136>(cfg, L, T, coef, dinv, b, x, nsweeps, done); break;
+        case 264: launch_gs_inst<D, 512, 1, 264>(cfg, L, T, coef, dinv, b, x, nsweeps, done); break;
+        default: launch_gs_inst<D, 512, 1, 0>(cfg, L, T, coef, dinv, b, x, nsweeps, done); break;
     }
-    if (g_gs_pf) { PDEOP_GS_DISPATCH(true) } else { PDEOP_GS_DISPATCH(false) }
-#undef PDEOP_GS_DISPATCH
 }
 
 template <int D>

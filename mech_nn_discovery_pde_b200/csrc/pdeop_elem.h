@@ -182,7 +182,8 @@ PDEOP_HD void k_neighbors(const LevelDev& L, const int* __restrict__ rowbase, co
         const double* xp = x + (1 + a) * G;
         const double* xq = x + (1 + D + a) * G;
         // phase 1: all 24 neighbour loads of this axis in flight together (one memory round trip per axis
-        // instead of one per neighbour: the kernels built on this body are latency-bound, not bandwidth-bound)
+        // instead of one per neighbour: the kernels built on this body are latency-bound, not bandwidth-bound).
+        // Batching all axes at once (needs >200 registers, 256-thread CTAs) was measured and is not faster.
         double un[8], pn[8], qn[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -211,49 +212,6 @@ PDEOP_HD void k_neighbors(const LevelDev& L, const int* __restrict__ rowbase, co
         acc[0] += au;
         acc[1 + a] += ap;
         acc[1 + D + a] += aq;
-    }
-}
-
-// Register-free memory parallelism: issue L1 prefetches for every vector address the point update will read
-// (neighbours of all axes + own point) before the gather starts.  No-op on the host.
-PDEOP_HD void prefetch_l1(const void* p) {
-#if defined(__CUDA_ARCH__)
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#else
-    (void)p;
-#endif
-}
-
-template <int D>
-PDEOP_HD void gs_prefetch(const LevelDev& L, const int* __restrict__ rowbase, const double* coef, const double* dinv,
-                          const double* b, const double* x, int w, int i0, int i1, int i2) {
-    const int G = L.G, N0 = L.N[0];
-    const int idx[3] = {i0, i1, i2};
-    const int* __restrict__ rb = rowbase + (i0 + i1 + i2 + 4) * N0 + i0;
-#pragma unroll
-    for (int m = 0; m < 1 + 2 * D; ++m) {
-        prefetch_l1(x + m * G + w);
-        prefetch_l1(b + m * G + w);
-        prefetch_l1(coef + m * G + w);
-        prefetch_l1(dinv + m * G + w);
-    }
-#pragma unroll
-    for (int a = 0; a < D; ++a) {
-        const int ax = 3 - D + a;
-        const int n = L.N[ax];
-        const int i = idx[ax];
-#pragma unroll
-        for (int o = -4; o <= 4; ++o) {
-            if (o == 0) continue;
-            if ((unsigned)(i + o) >= (unsigned)n) continue;
-            int wn;
-            if (ax == 2) wn = rb[o * N0] + i1;
-            else if (ax == 1) wn = rb[o * N0] + i1 + o;
-            else wn = rb[o * N0 + o] + i1;
-            prefetch_l1(x + wn);
-            prefetch_l1(x + (1 + a) * G + wn);
-            prefetch_l1(x + (1 + D + a) * G + wn);
-        }
     }
 }
 
@@ -360,7 +318,7 @@ PDEOP_HD void apply_k_elem(const LevelDev& L, const double* __restrict__ T, cons
 //   x_j <- (b_j - sum_{k != j} K_jk x_k) / K_jj   with already-updated values for k < j.
 // The equation-row part of the point block is rank one (c c^T): the running sum S = c.x is kept up to
 // date as channels are updated, and the division is a multiplication by the precomputed reciprocal diagonal.
-template <int D, class LD, int PITCH, bool PF = false>
+template <int D, class LD, int PITCH>
 PDEOP_HD void gs_elem(const LevelDev& L, const int* __restrict__ rowbase, const double* __restrict__ T,
                       const double* __restrict__ coef, const double* __restrict__ dinv,
                       const double* __restrict__ b, double* x, int w) {
@@ -368,7 +326,6 @@ PDEOP_HD void gs_elem(const LevelDev& L, const int* __restrict__ rowbase, const 
     const int G = L.G;
     int i0, i1, i2;
     unpack_coord(L.coord[w], i0, i1, i2);
-    if (PF) gs_prefetch<D>(L, rowbase, coef, dinv, b, x, w, i0, i1, i2);
     const bool eq = L.flags[w] & 1;
     // own-point loads first: their latency overlaps the neighbour gathers
     double xl[M], c[M], bl[M], di[M];
@@ -384,31 +341,39 @@ PDEOP_HD void gs_elem(const LevelDev& L, const int* __restrict__ rowbase, const 
     k_neighbors<D, LD, PITCH>(L, rowbase, T, x, i0, i1, i2, acc);
     PointLocal<D> pl;
     load_axis_local<D, PITCH>(T, i0, i1, i2, pl);
-    double S = 0.0;
+    // Canonical arithmetic (every kernel that inlines this body, and the host emulator, produce the same bits):
+    //   S   = ((c_u x_u + s_0) + s_1) + ...,   s_a = fma(c_qa, x_qa, c_pa x_pa)
+    //   u   : off = c_u t + l_0 + l_1 + ...,   l_a = fma(uq_a, x_qa, up_a x_pa)
+    //   p_a : off = fma(pq_a, x_qa, fma(up_a, x_u, c_pa t));   q_a : off = fma(pq_a, x_pa, fma(uq_a, x_u, c_qa t))
+    //   with t = fma(-c_m, x_m, S),  x_m <- (r_m - off) * dinv_m,  S <- fma(c_m, x_m, t)
 #pragma unroll
-    for (int m = 0; m < M; ++m) {
-        acc[m] = bl[m] - acc[m];
-        S = fma(c[m], xl[m], S);
+    for (int m = 0; m < M; ++m) acc[m] = bl[m] - acc[m];
+    double S = c[0] * xl[0];
+#pragma unroll
+    for (int a = 0; a < D; ++a) S = S + fma(c[1 + D + a], xl[1 + D + a], c[1 + a] * xl[1 + a]);
+    {   // u
+        const double t = fma(-c[0], xl[0], S);
+        double off = c[0] * t;
+#pragma unroll
+        for (int a = 0; a < D; ++a) off = off + fma(pl.uq[a], xl[1 + D + a], pl.up[a] * xl[1 + a]);
+        const double xn = (acc[0] - off) * di[0];
+        S = fma(c[0], xn, t);
+        xl[0] = xn;
     }
 #pragma unroll
-    for (int m = 0; m < M; ++m) {
-        const double t = fma(-c[m], xl[m], S);      // sum_{k != m} c_k x_k
-        double off = c[m] * t;
-        if (m == 0) {
+    for (int a = 0; a < D; ++a) {   // u_c channels
+        const int m = 1 + a;
+        const double t = fma(-c[m], xl[m], S);
+        const double off = fma(pl.pq[a], xl[1 + D + a], fma(pl.up[a], xl[0], c[m] * t));
+        const double xn = (acc[m] - off) * di[m];
+        S = fma(c[m], xn, t);
+        xl[m] = xn;
+    }
 #pragma unroll
-            for (int a = 0; a < D; ++a) {
-                off = fma(pl.up[a], xl[1 + a], off);
-                off = fma(pl.uq[a], xl[1 + D + a], off);
-            }
-        } else if (m <= D) {
-            const int a = m - 1;
-            off = fma(pl.up[a], xl[0], off);
-            off = fma(pl.pq[a], xl[1 + D + a], off);
-        } else {
-            const int a = m - 1 - D;
-            off = fma(pl.uq[a], xl[0], off);
-            off = fma(pl.pq[a], xl[1 + a], off);
-        }
+    for (int a = 0; a < D; ++a) {   // u_cc channels
+        const int m = 1 + D + a;
+        const double t = fma(-c[m], xl[m], S);
+        const double off = fma(pl.pq[a], xl[1 + a], fma(pl.uq[a], xl[0], c[m] * t));
         const double xn = (acc[m] - off) * di[m];
         S = fma(c[m], xn, t);
         xl[m] = xn;
