@@ -194,7 +194,7 @@ void be_apply_k(stream_t st, const LevelDev& L, int B, const double* T, const do
 // together with the level's rowbase/hstart index tables: the cluster barrier invalidates L1 every step, so
 // anything read from global memory is re-fetched from L2 each step, while shared memory stays put.
 // PS == 0: tables too large for shared memory, read from global memory.
-template <int D, int THREADS, int MINB, class LD, int PS>
+template <int D, int THREADS, int MINB, class LD, int PS, bool SINGLE>
 __global__ void __launch_bounds__(THREADS, MINB) k_gs_cluster(LevelDev L, const double* __restrict__ T,
                                                               const double* __restrict__ coef,
                                                               const double* __restrict__ dinv,
@@ -202,9 +202,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gs_cluster(LevelDev L, const 
                                                               const int* done) {
     if (done && *done) return;
     extern __shared__ __align__(16) unsigned char gs_smem[];
+    // SINGLE: one CTA per instance (small levels): block barrier, no L1 invalidation between steps
     cg::cluster_group cluster = cg::this_cluster();
-    const int csize = (int)cluster.num_blocks();
-    const int rank = (int)cluster.block_rank();
+    const int csize = SINGLE ? 1 : (int)cluster.num_blocks();
+    const int rank = SINGLE ? 0 : (int)cluster.block_rank();
     const int ib = blockIdx.x / csize;
     const int tid = rank * blockDim.x + threadIdx.x;
     const int nthreads = csize * blockDim.x;
@@ -221,8 +222,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gs_cluster(LevelDev L, const 
         int* hss = rbs + nrb;
         int maxn = L.N[0] > L.N[1] ? L.N[0] : L.N[1];
         maxn = (maxn > L.N[2] ? maxn : L.N[2]) + 2 * kTabPad;
+        constexpr int PSD = PS > 0 ? PS : 1;
         for (int i = threadIdx.x; i < D * kTabEntries * PS; i += blockDim.x) {
-            const int row = i / PS, pos = i - row * PS;
+            const int row = i / PSD, pos = i - row * PSD;
             Ts[i] = pos < maxn ? Ti[(size_t)row * kTabPitch + pos] : 0.0;
         }
         for (int i = threadIdx.x; i < nrb; i += blockDim.x) rbs[i] = L.rowbase[i - 4];
@@ -259,7 +261,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gs_cluster(LevelDev L, const 
         }
         // release/acquire at cluster scope; the acquire side invalidates L1 (CCTL.IVALL), so the next
         // step's plain loads of x see what the other CTAs of the cluster wrote in this one
-        cluster.sync();
+        if (SINGLE) __syncthreads();
+        else cluster.sync();
     }
 }
 
@@ -293,18 +296,21 @@ static int num_sms() {
 }
 
 // tuning switch (read once): PDEOP_GS_SMEM = 0 disables the shared-memory staging of the tables (A/B testing)
-static int g_gs_threads = 0, g_gs_smem = 1;
+// PDEOP_GS_SINGLE = n: levels whose busiest step has at most n*512 points run with one CTA per instance
+static int g_gs_threads = 0, g_gs_smem = 1, g_gs_single = 0;
 static void gs_tuning() {
     if (g_gs_threads) return;
     g_gs_threads = 512;   // 128 registers/thread; 256/384/1024-thread variants were measured and are not faster
     const char* m = getenv("PDEOP_GS_SMEM");
     g_gs_smem = (m && atoi(m) == 0) ? 0 : 1;
+    const char* sg = getenv("PDEOP_GS_SINGLE");
+    g_gs_single = sg ? atoi(sg) : 0;
 }
 
-template <int D, int THREADS, int MINB, int PS>
+template <int D, int THREADS, int MINB, int PS, bool SINGLE>
 static void launch_gs_inst(cudaLaunchConfig_t& cfg, const LevelDev& L, const double* T, const double* coef,
                            const double* dinv, const double* b, double* x, int nsweeps, const int* done) {
-    auto kern = k_gs_cluster<D, THREADS, MINB, LdPlain, PS>;
+    auto kern = k_gs_cluster<D, THREADS, MINB, LdPlain, PS, SINGLE>;
     size_t smem = 0;
     if (PS > 0) {
         smem = (size_t)D * kTabEntries * PS * sizeof(double) + ((size_t)(L.S + 8) * L.N[0] + 8 + L.S + 1) * sizeof(int);
@@ -348,6 +354,8 @@ static void launch_gs_cluster(cudaStream_t s, const LevelDev& L, int B, const do
     int fit = per_sm * num_sms() / (B > 0 ? B : 1);
     int csize = 1;
     while (csize * 2 <= 8 && csize * 2 <= fit && csize < want) csize *= 2;
+    const bool single = csize == 1 || want <= g_gs_single;
+    if (single) csize = 1;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(B * csize));
@@ -360,13 +368,16 @@ static void launch_gs_cluster(cudaStream_t s, const LevelDev& L, int B, const do
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    switch (ps) {
-        case 40: launch_gs_inst<D, 512, 1, 40>(cfg, L, T, coef, dinv, b, x, nsweeps, done); break;
-        case 72: launch_gs_inst<D, 512, 1, 72>(cfg, L, T, coef, dinv, b, x, nsweeps, done); break;
-        case 136: launch_gs_inst<D, 512, 1, 136>(cfg, L, T, coef, dinv, b, x, nsweeps, done); break;
-        case 264: launch_gs_inst<D, 512, 1, 264>(cfg, L, T, coef, dinv, b, x, nsweeps, done); break;
-        default: launch_gs_inst<D, 512, 1, 0>(cfg, L, T, coef, dinv, b, x, nsweeps, done); break;
+#define PDEOP_GS_DISPATCH(SG)                                                                            \
+    switch (ps) {                                                                                        \
+        case 40: launch_gs_inst<D, 512, 1, 40, SG>(cfg, L, T, coef, dinv, b, x, nsweeps, done); break;   \
+        case 72: launch_gs_inst<D, 512, 1, 72, SG>(cfg, L, T, coef, dinv, b, x, nsweeps, done); break;   \
+        case 136: launch_gs_inst<D, 512, 1, 136, SG>(cfg, L, T, coef, dinv, b, x, nsweeps, done); break; \
+        case 264: launch_gs_inst<D, 512, 1, 264, SG>(cfg, L, T, coef, dinv, b, x, nsweeps, done); break; \
+        default: launch_gs_inst<D, 512, 1, 0, SG>(cfg, L, T, coef, dinv, b, x, nsweeps, done); break;    \
     }
+    if (single) { PDEOP_GS_DISPATCH(true) } else { PDEOP_GS_DISPATCH(false) }
+#undef PDEOP_GS_DISPATCH
 }
 
 template <int D>
