@@ -8,6 +8,9 @@ the native plan (csrc/pdeop_solver.cpp).  This class keeps the attributes caller
 from itertools import combinations
 
 import numpy as np
+import torch
+
+from .line_values import line_values
 
 
 class QPVariableSet:
@@ -88,6 +91,8 @@ class PDESYSLP:
                                       + self.num_added_derivative_constraints)
         self.num_constraints = self.num_added_constraints
         self.tc_count = order + 2
+        self._eq_g = None
+        self.plan = None   # native plan, attached by the layer that owns this object
         step_coords = np.array(self.coord_dims)
         self.step_grid_size = {}
         self.step_grid_shape = {}
@@ -95,6 +100,46 @@ class PDESYSLP:
             one_hot = np.array([1 if k == i else 0 for k in range(d)])
             self.step_grid_size[i] = int(np.prod(step_coords - one_hot))
             self.step_grid_shape[i] = tuple(int(v) for v in (step_coords - one_hot))
+
+    # ---- per-call constraint values (the reference returns torch.sparse tensors here; the kernels consume
+    # ---- the same numbers un-expanded, so these return dense carriers) -------------------------------------
+    def equation_grid_pointers(self, device=None):
+        """C-order grid pointers of the points that carry an equation row: first-axis index >= 1 and strictly
+        inside every other axis (lp_pde_central_diff.py:228-235, 748-764)."""
+        if self._eq_g is None:
+            idx = np.indices(self.coord_dims).reshape(self.n_coord, -1)
+            keep = idx[0] != 0
+            for c in range(1, self.n_coord):
+                keep &= (idx[c] != 0) & (idx[c] != self.coord_dims[c] - 1)
+            self._eq_g = torch.as_tensor(np.nonzero(keep)[0], dtype=torch.long)
+            assert self._eq_g.numel() == self.num_added_equation_constraints
+        if device is not None and self._eq_g.device != device:
+            self._eq_g = self._eq_g.to(device)
+        return self._eq_g
+
+    def remove_pad(self, values, coeffs=True):
+        """(B, G, M) -> (B, n_eq, M) or (B, G) -> (B, n_eq): rows of the interior points (:1686-1705)."""
+        g = self.equation_grid_pointers(values.device)
+        if coeffs:
+            return values.reshape(self.bs, self.var_set.grid_size, -1).index_select(1, g)
+        return values.reshape(self.bs, self.var_set.grid_size).index_select(1, g)
+
+    def add_pad(self, eq_values):
+        """(B, n_eq) -> (B, *coord_dims) with zeros on the rows that carry no equation (:1632-1647); fp64."""
+        g = self.equation_grid_pointers(eq_values.device)
+        out = eq_values.new_zeros(eq_values.shape[0], self.var_set.grid_size)
+        out.index_copy_(1, g, eq_values)
+        return out.reshape(eq_values.shape[0], *self.coord_dims)
+
+    def build_equation_tensor(self, coeffs):
+        """Values of the equation rows, (B, n_eq, M), in the reference's value order (row-major over equation
+        rows, then multi-index; :1707-1719).  Dense carrier instead of torch.sparse_coo_tensor."""
+        return self.remove_pad(coeffs, coeffs=True)
+
+    def build_derivative_tensor(self, steps_list):
+        """Values of the derivative rows per line position: (central (B,Ntot,2,6), forward (B,Ftot,4), backward
+        (B,Ftot,4)) -- build_derivative_values (:1618-1630) before its expansion over the grid."""
+        return line_values(steps_list)
 
     def get_solution_reshaped(self, x):
         """(B, n) -> (B, G, M)  (lp_pde_central_diff.py:486-494)."""

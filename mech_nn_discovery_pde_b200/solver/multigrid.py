@@ -6,7 +6,8 @@ import torch
 import torch.nn as nn
 
 from ..config import PDEConfig
-from ..ops import MGSolveFn, PdePlan, new_holder
+from ..ops import PdePlan
+from . import qp_dual_sparse_multigrid_normal_kkt as MGS
 from .line_values import coarsen_steps, line_values
 from .lp_pde_central_diff import PDESYSLP
 
@@ -81,11 +82,23 @@ class MultigridLayer(nn.Module):
                                          solver_dbl=True, n_grid=n_grid, evolution=evolution,
                                          downsample_first=downsample_first, device=None, _library=_library)
         self.pde = self.mg_solver.pde_list[0]
+        self.pde.plan = self.mg_solver.plan
         self.n_orders = len(self.pde.var_set.mi_list)
         self.grid_size = self.pde.var_set.grid_size
         self.step_grid_shape = self.pde.step_grid_shape
-        self.config = PDEConfig
-        self.last_holder = None
+        self.qpf = MGS.QPFunction(self.pde, self.mg_solver, self.n_iv, gamma=gamma, alpha=alpha, double_ret=double_ret)
+
+    @property
+    def config(self):
+        return self.qpf.config
+
+    @config.setter
+    def config(self, value):
+        self.qpf.config = value
+
+    @property
+    def last_holder(self):
+        return self.qpf.last_holder
 
     def forward(self, coeffs, rhs, iv_rhs, steps_list):
         B = self.bs * self.n_ind_dim
@@ -104,11 +117,10 @@ class MultigridLayer(nn.Module):
         iv_rhs = iv_rhs.double()
         steps = [s.double() for s in steps_list]
 
-        cv, fv, bv = line_values(steps)
-        coarse = self.mg_solver.coarse_line_values(steps)
-        holder = new_holder(self.mg_solver.plan, coarse, self.config)
-        x = MGSolveFn.apply(coeffs, rhs, iv_rhs, cv, fv, bv, holder)
-        self.last_holder = holder
+        # same call sequence as the reference (multigrid.py:607-611)
+        derivative_constraints = self.pde.build_derivative_tensor(steps)
+        eq_constraints = self.pde.build_equation_tensor(coeffs)
+        x = self.qpf(eq_constraints, rhs, iv_rhs, derivative_constraints, coeffs, steps)
         eps = None
         u = self.pde.get_solution_reshaped(x)
         u = u.reshape(self.bs, self.n_ind_dim, *u.shape[1:])

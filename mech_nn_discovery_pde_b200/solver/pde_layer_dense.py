@@ -4,9 +4,8 @@ B200-native dense path.  Same constructor, same ``forward(coeffs, rhs, iv_rhs, s
 import torch
 import torch.nn as nn
 
-from ..config import PDEConfig
-from ..ops import DenseSolveFn, PdePlan, new_holder
-from .line_values import line_values
+from ..ops import PdePlan
+from . import qp_dual_dense_normal_kkt as MGS
 from .lp_pde_central_diff import PDESYSLP
 
 
@@ -35,11 +34,23 @@ class PDEDenseLayer(nn.Module):
         # (pde_layer_dense.py:72-75)
         self.pde = PDESYSLP(bs * n_ind_dim, self.coord_dims, order, n_iv, init_index_mi_list, self.plan.n_init,
                             evolution=False, dtype=torch.float64)
+        self.pde.plan = self.plan
         self.n_orders = len(self.pde.var_set.mi_list)
         self.grid_size = self.pde.var_set.grid_size
         self.step_grid_shape = self.pde.step_grid_shape
-        self.config = PDEConfig
-        self.last_holder = None
+        self.qpf = MGS.QPFunction(self.pde, double_ret=double_ret)
+
+    @property
+    def config(self):
+        return self.qpf.config
+
+    @config.setter
+    def config(self, value):
+        self.qpf.config = value
+
+    @property
+    def last_holder(self):
+        return self.qpf.last_holder
 
     def forward(self, coeffs, rhs, iv_rhs, steps_list):
         B = self.bs * self.n_ind_dim
@@ -56,10 +67,10 @@ class PDEDenseLayer(nn.Module):
         iv_rhs = iv_rhs.double()
         steps = [s.double() for s in steps_list]
 
-        cv, fv, bv = line_values(steps)
-        holder = new_holder(self.plan, [], self.config)
-        x = DenseSolveFn.apply(coeffs, rhs, iv_rhs, cv, fv, bv, holder)
-        self.last_holder = holder
+        # same call sequence as the reference (pde_layer_dense.py:107-110)
+        derivative_constraints = self.pde.build_derivative_tensor(steps)
+        eq_constraints = self.pde.build_equation_tensor(coeffs)
+        x = self.qpf(eq_constraints, rhs, iv_rhs, derivative_constraints, coeffs, steps)
         eps = None
         u = self.pde.get_solution_reshaped(x)
         u = u.reshape(self.bs, self.n_ind_dim, *u.shape[1:])

@@ -111,3 +111,56 @@ def test_rhs_grad_fp32_quirk_and_knobs():
         mg_fgmres_max_iter_backward = 10
     z, out = run_layer_case(lib, "cpu", "mg_2d_16x16_g2", config=Short)
     assert int(out["info_fwd"][0]) == 20 and int(out["info_bwd"][0]) == 10
+
+
+def test_qpfunction_factory_surface():
+    """The reference's QPFunction factories and pde.build_*_tensor helpers: gradients go to the constraint values,
+    rhs and iv_rhs, none to coeffs / steps_list (qp_dual_sparse_multigrid_normal_kkt.py:162)."""
+    import torch
+    from mech_nn_discovery_pde_b200 import MultigridLayer
+    from mech_nn_discovery_pde_b200.solver.qp_dual_sparse_multigrid_normal_kkt import QPFunction
+    lib = emu_library()
+    z, dims, steps = load_layer_case("mg_2d_16x16_g2")
+    B = int(z["bs"])
+    layer = MultigridLayer(bs=B, coord_dims=dims, order=2, n_ind_dim=1, n_iv=1, n_grid=2, downsample_first=True,
+                           init_index_mi_list=IV_LISTS["burgers"], n_iv_steps=1, _library=lib)
+    pde, mg = layer.pde, layer.mg_solver
+    qpf = QPFunction(pde, mg, 1)
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64)
+    coeffs = t(z["coeffs"]).requires_grad_(True)
+    steps_t = [t(s).requires_grad_(True) for s in steps]
+    eq = pde.build_equation_tensor(coeffs.detach()).requires_grad_(True)
+    assert eq.shape == (B, pde.num_added_equation_constraints, layer.n_orders)
+    dc = tuple(v.detach().requires_grad_(True) for v in pde.build_derivative_tensor(steps_t))
+    rhs = t(z["rhs"]).requires_grad_(True)
+    x = qpf(eq, rhs, t(z["iv_rhs"]), dc, coeffs, steps_t)
+    assert x.shape == (B, pde.var_set.num_vars)
+    assert rel(x.detach().numpy().reshape(B, 1, -1, layer.n_orders), z["u"]) < 1e-8
+    (x * t(z["loss_w"]).reshape(B, -1)).sum().backward()
+    assert coeffs.grad is None and all(s.grad is None for s in steps_t)
+    # dA restricted to the equation rows == reference's d_coeffs on those rows
+    g = pde.equation_grid_pointers().numpy()
+    assert rel(eq.grad.numpy(), z["d_coeffs"][:, g, :]) < 1e-8
+    assert rel(rhs.grad.numpy(), z["d_rhs"]) < 1e-8
+    # pad helpers round trip (lp_pde_central_diff.py:1632-1705)
+    r = pde.remove_pad(rhs.detach(), coeffs=False)
+    back = pde.add_pad(r).reshape(B, -1)
+    mask = np.zeros(pde.var_set.grid_size, bool)
+    mask[g] = True
+    assert np.array_equal(back.numpy()[:, mask], rhs.detach().numpy()[:, mask]) and (back.numpy()[:, ~mask] == 0).all()
+
+
+def test_n_ind_dim_batches_like_reference():
+    """n_ind_dim > 1 multiplies the batch: (bs, n_ind_dim) instances share one block system (multigrid.py:589-605)."""
+    import torch
+    from mech_nn_discovery_pde_b200 import MultigridLayer
+    lib = emu_library()
+    z, dims, steps = load_layer_case("mg_2d_16x16_g2")   # batch 2 -> bs=1, n_ind_dim=2
+    layer = MultigridLayer(bs=1, coord_dims=dims, order=2, n_ind_dim=2, n_iv=1, n_grid=2, downsample_first=True,
+                           init_index_mi_list=IV_LISTS["burgers"], n_iv_steps=1, _library=lib)
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64)
+    G, M = layer.grid_size, layer.n_orders
+    u0, u, eps = layer(t(z["coeffs"]).reshape(1, 2, G, M), t(z["rhs"]).reshape(1, 2, G), t(z["iv_rhs"]).reshape(1, 2, -1),
+                       [t(s).reshape(1, 2, -1) for s in steps])
+    assert u.shape == (1, 2, G, M) and u0.shape == (1, 2, G) and eps is None
+    assert rel(u.detach().numpy().reshape(2, 1, G, M), z["u"]) < 1e-8
