@@ -164,3 +164,55 @@ def test_n_ind_dim_batches_like_reference():
                        [t(s).reshape(1, 2, -1) for s in steps])
     assert u.shape == (1, 2, G, M) and u0.shape == (1, 2, G) and eps is None
     assert rel(u.detach().numpy().reshape(2, 1, G, M), z["u"]) < 1e-8
+
+
+def _fgmres_call(lib, device, plan, persist, scratch, b, cfg):
+    import ctypes
+    import torch
+    dev = torch.device(device)
+    bt = torch.as_tensor(b, dtype=torch.float64, device=dev).contiguous()
+    x = torch.zeros_like(bt)
+    info = torch.zeros(4, dtype=torch.float64, device=dev)
+    hess = torch.zeros((cfg.restart + 1) * cfg.restart, dtype=torch.float64, device=dev)
+    lib.check(lib.dll.pdeop_fgmres(plan.handle, ctypes.byref(cfg), 0, _lib._ptr(bt), _lib._ptr(x), _lib._ptr(info),
+                                   _lib._ptr(hess), _lib._ptr(persist), _lib._ptr(scratch),
+                                   _lib.current_stream_ptr(dev)))
+    return x.cpu().numpy(), info.cpu().numpy(), hess.cpu().numpy().reshape(cfg.restart + 1, cfg.restart)
+
+
+def check_fgmres_control_flow(lib, device):
+    """Device-side convergence flag (fgmres.py:76-78,134): zero rhs returns zeros with 0 iterations; a loose
+    tolerance stops after the first restart cycle; the Hessenberg matrix matches the oracle's."""
+    from oracle import pde_oracle as O
+    z, dims, steps = load_layer_case("mg_2d_16x16_g2")
+    iv = IV_LISTS[str(z["iv_name"])]
+    B = int(z["bs"])
+    sr = StageRunner(lib, device, dims, iv, B, 2, True, z["coeffs"], steps)
+    mg = O.mg_setup(dims, iv, z["coeffs"], z["rhs"], z["iv_rhs"], steps, 2, True)
+    n = B * sr.plan.n
+    cfg = sr.plan.cfg(False)
+    x, info, _ = _fgmres_call(lib, device, sr.plan, sr.persist, sr.scratch, np.zeros(n), cfg)
+    assert int(info[0]) == 0 and not x.any()
+    rng = np.random.default_rng(0)
+    b = mg.K_list[0] @ rng.standard_normal(n)       # consistent right-hand side
+    # reference run, full length, with trace
+    tr = {}
+    xr, (it_r, rn_r) = O.fgmres(mg.K_list[0], b, lambda v: O.v_cycle_start(mg, v), restart=10, maxiter=40, trace=tr)
+    x, info, H = _fgmres_call(lib, device, sr.plan, sr.persist, sr.scratch, b, cfg)
+    assert int(info[0]) == it_r and abs(info[1] - rn_r) <= 1e-6 * rn_r
+    assert rel(x, xr) < 1e-8
+    assert rel(H, tr["H"][-1]) < 1e-7                      # Hessenberg of the last restart cycle
+    # loose absolute tolerance: stop at the first residual check that passes (after k+1 restart cycles)
+    rn = tr["r_norms"]
+    k = next(i for i in range(len(rn) - 1) if rn[i + 1] < 0.9 * rn[i])
+    cfg2 = sr.plan.cfg(False)
+    cfg2.atol = float(0.5 * (rn[k] + rn[k + 1]))
+    x1, info1, _ = _fgmres_call(lib, device, sr.plan, sr.persist, sr.scratch, b, cfg2)
+    assert int(info1[0]) == 10 * (k + 1) and abs(info1[1] - rn[k + 1]) <= 1e-6 * rn[k + 1]
+    x1r, (it1, _) = O.fgmres(mg.K_list[0], b, lambda v: O.v_cycle_start(mg, v), restart=10, maxiter=40,
+                             atol=cfg2.atol)
+    assert it1 == 10 * (k + 1) and rel(x1, x1r) < 1e-8
+
+
+def test_fgmres_control_flow():
+    check_fgmres_control_flow(emu_library(), "cpu")

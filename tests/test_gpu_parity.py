@@ -281,3 +281,8 @@ def test_gl_scaling_grid_smoke(lib):
     assert torch.isfinite(u).all() and torch.isfinite(coeffs.grad).all()
     # the capped iterate still reduces the normal-equation residual by a large factor
     assert f[1] < 0.1 * float(layer.last_holder.info_fwd[2].item())
+
+
+def test_fgmres_control_flow(lib):
+    from tests.test_emu_structure import check_fgmres_control_flow
+    check_fgmres_control_flow(lib, "cuda:0")
