@@ -793,30 +793,41 @@ __global__ void __launch_bounds__(128) k_chol_trsm(int n, double* A, size_t stri
 }
 
 // C[i][j] -= sum_{t in [p0,p1)} A[i][t] A[j][t]   for i in [r0,r1), j in [c0,c1), i >= j
-// fp64 has no tcgen05 kind and DMMA's rate equals the FMA pipe's on B200, so this is a register-tiled DFMA
-// kernel: 128x128 tile per CTA, 8x8 accumulators per thread (4 FMAs per shared-memory load, the ratio the
-// 128 B/clk shared-memory pipe needs to keep 64 DFMA/clk busy), next K-chunk prefetched into registers
-// while the current one is multiplied.
+// Tensor-core path for fp64: mma.sync.m8n8k4.f64 (DMMA; fp64 has no tcgen05 kind).  128x128 tile per CTA, 8 warps
+// as 4 (rows) x 2 (columns), each warp a 32x64 sub-tile = 4x8 m8n8 accumulator tiles (64 doubles per lane).
+// Both operands come from the same row-major panel: A fragment = P[i][k], B fragment (column-major k x n) = P[j][k].
+// Shared tiles are [row][k] with a 20-double pitch: a half-warp's 64-bit fragment loads hit 32 distinct banks.
+// The next K-chunk is prefetched into registers while the current one is multiplied.
 constexpr int kSyrkT = 128;
 constexpr int kSyrkK = 16;
+constexpr int kSyrkLd = 20;
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
 __global__ void __launch_bounds__(256, 1) k_syrk(int n, double* A, size_t strideA, int r0, int r1, int c0, int c1,
                                                  int p0, int p1) {
     const int i0 = r0 + blockIdx.x * kSyrkT, j0 = c0 + blockIdx.y * kSyrkT;
     if (i0 + kSyrkT - 1 < j0) return;   // tile entirely above the diagonal
-    __shared__ __align__(16) double As[kSyrkK][kSyrkT];
-    __shared__ __align__(16) double Bs[kSyrkK][kSyrkT];
+    __shared__ double As[kSyrkT][kSyrkLd];
+    __shared__ double Bs[kSyrkT][kSyrkLd];
     double* Ab = A + (size_t)blockIdx.z * strideA;
     const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int wi = warp & 3, wj = warp >> 2;
+    const int gid = lane >> 2, tig = lane & 3;
     const int lr = tid >> 1, lk = (tid & 1) * 8;   // loader: row lr of the tile, 8 consecutive k
     const bool arow = i0 + lr < r1, brow = j0 + lr < c1;
     const double* ap = Ab + (size_t)(i0 + lr) * n + lk;
     const double* bp = Ab + (size_t)(j0 + lr) * n + lk;
-    double acc[8][8];
+    double acc[4][8][2];
 #pragma unroll
-    for (int a = 0; a < 8; ++a)
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
+        for (int b = 0; b < 8; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
     double ra[8], rb[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -827,8 +838,8 @@ __global__ void __launch_bounds__(256, 1) k_syrk(int n, double* A, size_t stride
     for (int kk = p0; kk < p1; kk += kSyrkK) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            As[lk + q][lr] = ra[q];
-            Bs[lk + q][lr] = rb[q];
+            As[lr][lk + q] = ra[q];
+            Bs[lr][lk + q] = rb[q];
         }
         __syncthreads();
         if (kk + kSyrkK < p1) {
@@ -840,32 +851,30 @@ __global__ void __launch_bounds__(256, 1) k_syrk(int n, double* A, size_t stride
             }
         }
 #pragma unroll
-        for (int k = 0; k < kSyrkK; ++k) {
-            double av[8], bv[8];
+        for (int ks = 0; ks < kSyrkK / 4; ++ks) {
+            double af[4], bf[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const double2 a2 = *reinterpret_cast<const double2*>(&As[k][ty * 2 + 32 * q]);
-                const double2 b2 = *reinterpret_cast<const double2*>(&Bs[k][tx * 2 + 32 * q]);
-                av[2 * q] = a2.x;
-                av[2 * q + 1] = a2.y;
-                bv[2 * q] = b2.x;
-                bv[2 * q + 1] = b2.y;
-            }
+            for (int mt = 0; mt < 4; ++mt) af[mt] = As[wi * 32 + mt * 8 + gid][ks * 4 + tig];
 #pragma unroll
-            for (int a = 0; a < 8; ++a)
+            for (int nt = 0; nt < 8; ++nt) bf[nt] = Bs[wj * 64 + nt * 8 + gid][ks * 4 + tig];
 #pragma unroll
-                for (int b = 0; b < 8; ++b) acc[a][b] += av[a] * bv[b];
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int a = 0; a < 8; ++a) {
-        const int i = i0 + ty * 2 + (a & 1) + 32 * (a >> 1);
+    for (int mt = 0; mt < 4; ++mt) {
+        const int i = i0 + wi * 32 + mt * 8 + gid;
         if (i >= r1) continue;
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const int j = j0 + tx * 2 + (b & 1) + 32 * (b >> 1);
-            if (j < c1 && i >= j) Ab[(size_t)i * n + j] -= acc[a][b];
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int j = j0 + wj * 64 + nt * 8 + 2 * tig + e;
+                if (j < c1 && i >= j) Ab[(size_t)i * n + j] -= acc[mt][nt][e];
+            }
         }
     }
 }
