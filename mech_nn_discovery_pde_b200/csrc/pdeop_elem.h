@@ -184,18 +184,26 @@ PDEOP_HD void k_neighbors(const LevelDev& L, const int* __restrict__ rowbase, co
         // phase 1: all 24 neighbour loads of this axis in flight together (one memory round trip per axis
         // instead of one per neighbour: the kernels built on this body are latency-bound, not bandwidth-bound).
         // Batching all axes at once (needs >200 registers, 256-thread CTAs) was measured and is not faster.
+        // Structural zeros: a derivative row reaches 3 or 4 positions away only through the one-sided stencils
+        // of the two positions next to either end (lp_pde_central_diff.py:1000-1006).  So for |o| >= 3 the
+        // couplings u(i) <-> u_c/u_cc(i+o) vanish unless position i+o is such an end position, and
+        // u_c/u_cc(i) <-> u(i+o) vanish unless i is.  Pure index tests: the skipped terms are exact zeros.
+        const bool i_end = i <= 1 || i >= n - 2;
         double un[8], pn[8], qn[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int o = j < 4 ? j - 4 : j - 3;
-            const bool ok = (unsigned)(i + o) < (unsigned)n;
+            const int ii = i + o;
+            const bool ok = (unsigned)ii < (unsigned)n;
+            const bool far = o < -2 || o > 2;
+            const bool okpq = ok && (!far || ii <= 1 || ii >= n - 2);
             int wn;
             if (ax == 2) wn = rb[o * N0] + i1;
             else if (ax == 1) wn = rb[o * N0] + i1 + o;
             else wn = rb[o * N0 + o] + i1;
             un[j] = ok ? LD::ld(xu + wn) : 0.0;
-            pn[j] = ok ? LD::ld(xp + wn) : 0.0;
-            qn[j] = ok ? LD::ld(xq + wn) : 0.0;
+            pn[j] = okpq ? LD::ld(xp + wn) : 0.0;
+            qn[j] = okpq ? LD::ld(xq + wn) : 0.0;
         }
         PDEOP_LOAD_FENCE();
         // phase 2: explicit fma => the same bits from every kernel that inlines this body and from the emulator
@@ -203,11 +211,17 @@ PDEOP_HD void k_neighbors(const LevelDev& L, const int* __restrict__ rowbase, co
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int o = j < 4 ? j - 4 : j - 3;
+            const int ii = i + o;
+            const bool far = o < -2 || o > 2;
             au = fma(Ta[(T_UU + o + 4) * PITCH], un[j], au);
-            au = fma(Ta[(T_UP - o + 4) * PITCH + o], pn[j], au);
-            au = fma(Ta[(T_UQ - o + 4) * PITCH + o], qn[j], au);
-            ap = fma(Ta[(T_UP + o + 4) * PITCH], un[j], ap);
-            aq = fma(Ta[(T_UQ + o + 4) * PITCH], un[j], aq);
+            if (!far || ii <= 1 || ii >= n - 2) {
+                au = fma(Ta[(T_UP - o + 4) * PITCH + o], pn[j], au);
+                au = fma(Ta[(T_UQ - o + 4) * PITCH + o], qn[j], au);
+            }
+            if (!far || i_end) {
+                ap = fma(Ta[(T_UP + o + 4) * PITCH], un[j], ap);
+                aq = fma(Ta[(T_UQ + o + 4) * PITCH], un[j], aq);
+            }
         }
         acc[0] += au;
         acc[1 + a] += ap;
