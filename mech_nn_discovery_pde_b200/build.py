@@ -19,6 +19,13 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
 
+def build_debug(out_path, extra_flags):
+    """Debug/experiment build into another path (e.g. tools/): never loaded by the package."""
+    cmd = [NVCC] + FLAGS + list(extra_flags) + ["-o", out_path] + [os.path.join(CSRC, f) for f in SOURCES]
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return out_path
+
+
 def build(force=False, verbose=False):
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(os.path.dirname(HERE), "include", "pdeop.h")]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):

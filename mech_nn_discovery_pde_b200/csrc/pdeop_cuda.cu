@@ -190,6 +190,16 @@ void be_apply_k(stream_t st, const LevelDev& L, int B, const double* T, const do
 // then the cluster barrier (release/acquire) orders the in-place iterate for the next step.
 // The iterate is read at the L2 coherence point (LdL2) because other CTAs of the cluster write it.
 // =================================================================================================
+#ifdef PDEOP_GS_TIMING
+// debug build only (tools/): [0] steps, [1] cycles in point updates, [2] cycles in the barrier, [3] point updates
+__device__ unsigned long long g_gs_dbg[8];
+extern "C" void pdeop_gs_dbg_read(unsigned long long* out) {
+    cudaMemcpyFromSymbol(out, g_gs_dbg, sizeof(g_gs_dbg));
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_gs_dbg, z, sizeof(z));
+}
+#endif
+
 // PS > 0: the instance's K tables are staged in shared memory with compile-time pitch PS (max extent + 8 <= PS),
 // together with the level's rowbase/hstart index tables: the cluster barrier invalidates L1 every step, so
 // anything read from global memory is re-fetched from L2 each step, while shared memory stays put.
@@ -246,6 +256,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gs_cluster(LevelDev L, const 
             const int s = t - kGsLag * k;
             total += hs[s + 1] - hs[s];
         }
+#ifdef PDEOP_GS_TIMING
+        const bool dbg = blockIdx.x == 0 && threadIdx.x == 0;
+        long long c0 = clock64();
+        int npts = 0;
+#endif
         for (int idx = tid; idx < total; idx += nthreads) {
             int rem = idx, w = -1;
             for (int k = k_lo; k <= k_hi; ++k) {
@@ -258,11 +273,26 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gs_cluster(LevelDev L, const 
                 rem -= cnt;
             }
             gs_elem<D, LD, PITCH>(L, rbuse, Tuse, coef + o, dinv + o, b + o, x + o, w);
+#ifdef PDEOP_GS_TIMING
+            ++npts;
+#endif
         }
+#ifdef PDEOP_GS_TIMING
+        long long c1 = clock64();
+#endif
         // release/acquire at cluster scope; the acquire side invalidates L1 (CCTL.IVALL), so the next
         // step's plain loads of x see what the other CTAs of the cluster wrote in this one
         if (SINGLE) __syncthreads();
         else cluster.sync();
+#ifdef PDEOP_GS_TIMING
+        if (dbg) {
+            long long c2 = clock64();
+            g_gs_dbg[0] += 1;
+            g_gs_dbg[1] += (unsigned long long)(c1 - c0);
+            g_gs_dbg[2] += (unsigned long long)(c2 - c1);
+            g_gs_dbg[3] += npts;
+        }
+#endif
     }
 }
 

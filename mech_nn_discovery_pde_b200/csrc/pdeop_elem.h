@@ -156,6 +156,20 @@ PDEOP_HD const double* axis_table(const double* T, int a) { return T + a * (kTab
 // ------------------------------------------------------------------------------------------------
 // PITCH: table pitch (kTabPitch for tables in global memory, a smaller compile-time pitch for the copy the
 // Gauss-Seidel kernel stages in shared memory); rowbase: L.rowbase or its shared-memory copy.
+#if defined(PDEOP_GS_TIMING) && defined(__CUDA_ARCH__)
+extern __device__ unsigned long long g_gs_dbg[8];
+#define PDEOP_TSTAMP(k)                                                       \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                                \
+        const long long now_ = clock64();                                    \
+        g_gs_dbg[k] += (unsigned long long)(now_ - tprev_);                   \
+        tprev_ = now_;                                                        \
+    }
+#define PDEOP_TSTART() long long tprev_ = clock64()
+#else
+#define PDEOP_TSTAMP(k)
+#define PDEOP_TSTART()
+#endif
+
 // keeps the compiler from sinking a batch of loads down to their first use (device only)
 #if defined(__CUDA_ARCH__)
 #define PDEOP_LOAD_FENCE() asm volatile("" ::: "memory")
@@ -338,9 +352,12 @@ PDEOP_HD void gs_elem(const LevelDev& L, const int* __restrict__ rowbase, const 
                       const double* __restrict__ b, double* x, int w) {
     constexpr int M = 1 + 2 * D;
     const int G = L.G;
+    PDEOP_TSTART();
     int i0, i1, i2;
     unpack_coord(L.coord[w], i0, i1, i2);
     const bool eq = L.flags[w] & 1;
+    if (eq && i0 < 0) return;   // (keeps the flag load before the timestamp)
+    PDEOP_TSTAMP(4);
     // own-point loads first: their latency overlaps the neighbour gathers
     double xl[M], c[M], bl[M], di[M];
 #pragma unroll
@@ -353,6 +370,8 @@ PDEOP_HD void gs_elem(const LevelDev& L, const int* __restrict__ rowbase, const 
     PDEOP_LOAD_FENCE();
     double acc[M];
     k_neighbors<D, LD, PITCH>(L, rowbase, T, x, i0, i1, i2, acc);
+    if (acc[0] == 1.2345e300) return;   // (forces the gather results before the timestamp)
+    PDEOP_TSTAMP(5);
     PointLocal<D> pl;
     load_axis_local<D, PITCH>(T, i0, i1, i2, pl);
     // Canonical arithmetic (every kernel that inlines this body, and the host emulator, produce the same bits):
@@ -394,6 +413,7 @@ PDEOP_HD void gs_elem(const LevelDev& L, const int* __restrict__ rowbase, const 
     }
 #pragma unroll
     for (int m = 0; m < M; ++m) x[m * G + w] = xl[m];
+    PDEOP_TSTAMP(6);
 }
 
 // ------------------------------------------------------------------------------------------------
