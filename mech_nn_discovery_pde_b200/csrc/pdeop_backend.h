@@ -36,9 +36,13 @@ void be_atb(stream_t st, const LevelDev& L, int B, const double* coef, const dou
 void be_apply_k(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, const double* x,
                 const double* b, double* y, int mode, const int* done);
 // nsweeps lexicographic Gauss-Seidel sweeps, in place.  variant 0: production kernel; 1: one launch per
-// hyperplane step (test cross-check).
+// hyperplane step (test cross-check).  stash: B * stash_stride doubles of scratch for the production kernel
+// (stash_stride >= be_gs_stash_doubles(L)).
 void be_gs(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, const double* dinv,
-           const double* b, double* x, int nsweeps, const int* done, int variant);
+           const double* b, double* x, double* stash, size_t stash_stride, int nsweeps, const int* done, int variant);
+// per-instance stash size: 8 doubles per point of the busiest step, rounded up to whole rounds of the largest
+// cluster (8 CTAs x 512 threads)
+inline size_t be_gs_stash_doubles(const LevelDev& L) { return 8 * ((size_t)L.G + 4096); }
 // dinv[m][w] = 1 / K[(w,m),(w,m)]: reciprocal diagonal of K, computed once per operator set-up
 void be_dinv(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, double* dinv);
 void be_dense(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, double* Kd);

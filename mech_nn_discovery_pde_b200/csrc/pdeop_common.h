@@ -25,7 +25,10 @@ constexpr int kTabPad = 4;        // stencil radius of K along an axis
 // Fixed table pitch (max extent 1023 + 2*4 padding, rounded): a compile-time constant so that every table
 // load of a stencil kernel is [position pointer + immediate offset] with no address arithmetic.
 constexpr int kTabPitch = 1032;
-constexpr int kGsLag = 5;         // hyperplane lag between pipelined Gauss-Seidel sweeps (radius + 1)
+// Hyperplane lag between pipelined Gauss-Seidel sweeps: radius + 2.  Radius + 1 keeps the sweeps independent; one
+// more lets the gather of step t+1 (everything but the backward distance-1 neighbours) run during step t, because
+// the farthest forward neighbour (s+1+4) was then finished by the previous sweep in step t-1, not in step t.
+constexpr int kGsLag = 6;
 constexpr int kMaxRestart = 32;
 constexpr int kSolveBlk = 256;    // block size of the dense triangular solves (inverse diagonal blocks)
 
@@ -45,7 +48,7 @@ struct LevelDev {
     int Ftot;        // sum of (active extents - 1)    (forward/backward row-value table length)
     int cvoff[3];    // per active axis a: offset into the central line table
     int fvoff[3];    // per active axis a: offset into the forward/backward line tables
-    const int* coord;    // [G]  i0 | i1<<10 | i2<<20, wave order
+    const int* coord;    // [G]  i0 | i1<<10 | i2<<20 | eq<<30 (eq: carries an equation row), wave order
     const int* flags;    // [G]  bit0: carries an equation row; bits 4+2m..5+2m: # initial rows on channel m
     const int* hstart;   // [S+1] first wave index of each hyperplane
     const int* rowbase;  // [(S+8)*N0] pos(i0,i1,i2) = rowbase[(s+4)*N0+i0] + i1  (4 spare ints either side)
@@ -63,6 +66,8 @@ PDEOP_HD void unpack_coord(int c, int& i0, int& i1, int& i2) {
     i1 = (c >> 10) & 1023;
     i2 = (c >> 20) & 1023;
 }
+
+PDEOP_HD bool coord_eq(int c) { return (c >> 30) & 1; }
 
 PDEOP_HD int wave_pos(const LevelDev& L, int i0, int i1, int i2) {
     return L.rowbase[(i0 + i1 + i2 + 4) * L.N[0] + i0] + i1;

@@ -256,11 +256,6 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gs_cluster(LevelDev L, const 
             const int s = t - kGsLag * k;
             total += hs[s + 1] - hs[s];
         }
-#ifdef PDEOP_GS_TIMING
-        const bool dbg = blockIdx.x == 0 && threadIdx.x == 0;
-        long long c0 = clock64();
-        int npts = 0;
-#endif
         for (int idx = tid; idx < total; idx += nthreads) {
             int rem = idx, w = -1;
             for (int k = k_lo; k <= k_hi; ++k) {
@@ -273,27 +268,237 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gs_cluster(LevelDev L, const 
                 rem -= cnt;
             }
             gs_elem<D, LD, PITCH>(L, rbuse, Tuse, coef + o, dinv + o, b + o, x + o, w);
-#ifdef PDEOP_GS_TIMING
-            ++npts;
-#endif
         }
-#ifdef PDEOP_GS_TIMING
-        long long c1 = clock64();
-#endif
         // release/acquire at cluster scope; the acquire side invalidates L1 (CCTL.IVALL), so the next
         // step's plain loads of x see what the other CTAs of the cluster wrote in this one
         if (SINGLE) __syncthreads();
         else cluster.sync();
-#ifdef PDEOP_GS_TIMING
-        if (dbg) {
-            long long c2 = clock64();
-            g_gs_dbg[0] += 1;
-            g_gs_dbg[1] += (unsigned long long)(c1 - c0);
-            g_gs_dbg[2] += (unsigned long long)(c2 - c1);
-            g_gs_dbg[3] += npts;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Software-pipelined wavefront Gauss-Seidel (production kernel).
+//
+// A point update needs exactly D*3 values written in the immediately preceding step: u, u_c, u_cc of the
+// backward distance-1 neighbour along each axis.  Everything else it reads (the other 7 offsets per axis, b)
+// was final one step earlier (kGsLag = radius + 2).  So each step is split in two halves around a SPLIT
+// cluster barrier:
+//     A(t): finish the points of step t   = stashed partial residual - backward-1 couplings, channel solve, store
+//     barrier.cluster.arrive.release
+//     B(t): pre-gather for the points of step t+1 (gs_pre_elem) into the stash; L2 prefetch of what A(t+1) reads
+//     barrier.cluster.wait.acquire
+// The critical path between two barriers is one batch of loads plus the channel solve; the long gather runs in
+// the shadow of the barrier and of the other CTAs' A halves.  The stash of a thread's first point of a step stays
+// in registers; further points (levels whose busiest step has more points than the cluster has threads) go through
+// a small per-thread global stash that stays L2 resident (it is rewritten every step).
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cluster_arrive_release() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait_acquire() {
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+constexpr int kStashSlots = 8;   // doubles per stashed point: M <= 7 residuals + (wave index, coord) packed
+
+template <int D, int THREADS, int PS, bool SINGLE>
+__global__ void __launch_bounds__(THREADS, 1) k_gs_pipe(LevelDev L, const double* __restrict__ T,
+                                                        const double* __restrict__ coef,
+                                                        const double* __restrict__ dinv,
+                                                        const double* __restrict__ b, double* x, double* stash,
+                                                        size_t stash_stride, int nsweeps, const int* done) {
+    if (done && *done) return;
+    constexpr int M = 1 + 2 * D;
+    extern __shared__ __align__(16) unsigned char gs_smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int csize = SINGLE ? 1 : (int)cluster.num_blocks();
+    const int rank = SINGLE ? 0 : (int)cluster.block_rank();
+    const int ib = blockIdx.x / csize;
+    const int tid = rank * blockDim.x + threadIdx.x;
+    const int nthreads = csize * blockDim.x;
+    const size_t o = (size_t)ib * L.M * L.G;
+    const double* Ti = T + (size_t)ib * L.D * kTabEntries * kTabPitch;
+    constexpr int PITCH = PS > 0 ? PS : kTabPitch;
+    const double* Tuse = Ti;
+    const int* rbuse = L.rowbase;
+    const int* hs = L.hstart;
+    // shared memory: [first-point stash: kStashSlots x THREADS doubles | K tables | rowbase | hstart]
+    double* st0 = reinterpret_cast<double*>(gs_smem) + threadIdx.x;
+    if (PS > 0) {
+        double* Ts = reinterpret_cast<double*>(gs_smem) + kStashSlots * THREADS;
+        int* rbs = reinterpret_cast<int*>(Ts + D * kTabEntries * PS);
+        const int nrb = (L.S + 8) * L.N[0] + 8;
+        int* hss = rbs + nrb;
+        int maxn = L.N[0] > L.N[1] ? L.N[0] : L.N[1];
+        maxn = (maxn > L.N[2] ? maxn : L.N[2]) + 2 * kTabPad;
+        constexpr int PSD = PS > 0 ? PS : 1;
+        for (int i = threadIdx.x; i < D * kTabEntries * PS; i += blockDim.x) {
+            const int row = i / PSD, pos = i - row * PSD;
+            Ts[i] = pos < maxn ? Ti[(size_t)row * kTabPitch + pos] : 0.0;
         }
+        for (int i = threadIdx.x; i < nrb; i += blockDim.x) rbs[i] = L.rowbase[i - 4];
+        for (int i = threadIdx.x; i <= L.S; i += blockDim.x) hss[i] = L.hstart[i];
+        __syncthreads();
+        Tuse = Ts;
+        rbuse = rbs + 4;
+        hs = hss;
+    }
+    const double* bo = b + o;
+    const double* co = coef + o;
+    const double* dvo = dinv + o;
+    double* xo = x + o;
+    double* st = stash + (size_t)ib * stash_stride + tid;
+    // opaque per-instance base pointers: keeps every access at [64-bit base + 32-bit element index] (one
+    // IMAD.WIDE.U32) instead of re-deriving base + instance offset + index in 64-bit arithmetic per load
+    asm volatile("" : "+l"(bo), "+l"(co), "+l"(dvo), "+l"(xo), "+l"(st));
+    __builtin_assume(__isGlobal(bo));
+    __builtin_assume(__isGlobal(co));
+    __builtin_assume(__isGlobal(dvo));
+    __builtin_assume(__isGlobal(xo));
+    __builtin_assume(__isGlobal(st));
+    const int G = L.G;
+    const int steps = L.S + kGsLag * (nsweeps - 1);
+
+    // points of step t: the hyperplanes s_k = t - lag*k of the sweeps k in flight, concatenated
+    auto step_sweeps = [&](int t, int& k_lo, int& k_hi) -> int {
+        k_lo = (t - (L.S - 1) + kGsLag - 1) / kGsLag;
+        if (k_lo < 0) k_lo = 0;
+        k_hi = t / kGsLag;
+        if (k_hi > nsweeps - 1) k_hi = nsweeps - 1;
+        int total = 0;
+        for (int k = k_lo; k <= k_hi; ++k) {
+            const int s = t - kGsLag * k;
+            total += hs[s + 1] - hs[s];
+        }
+        return total;
+    };
+    auto point_of = [&](int t, int k_lo, int k_hi, int idx) -> int {
+        int rem = idx;
+        for (int k = k_lo; k <= k_hi; ++k) {
+            const int s = t - kGsLag * k;
+            const int h0 = hs[s], cnt = hs[s + 1] - h0;
+            if (rem < cnt) return h0 + rem;
+            rem -= cnt;
+        }
+        return -1;
+    };
+    // this thread's first point of the step after the one being pre-gathered, and its coordinates: loaded a
+    // whole half-step before they are needed
+    int wN = -1, cfN = 0;
+    auto first_point = [&](int t) {
+        wN = -1;
+        cfN = 0;
+        if (t < steps) {
+            int k_lo, k_hi;
+            const int total = step_sweeps(t, k_lo, k_hi);
+            if (tid < total) {
+                wN = point_of(t, k_lo, k_hi, tid);
+                cfN = L.coord[wN];
+            }
+        }
+    };
+
+    // B half: pre-gather every point this thread owns in step t; returns how many
+    auto pregather = [&](int t) -> int {
+        int k_lo, k_hi;
+        const int total = step_sweeps(t, k_lo, k_hi);
+        int w = wN, cf = cfN;
+        first_point(t + 1);
+        int n = 0;
+        while (w >= 0) {
+            // coordinates of the next point of this step: in flight during this point's gather
+            const int idx_next = tid + (n + 1) * nthreads;
+            const int w_next = idx_next < total ? point_of(t, k_lo, k_hi, idx_next) : -1;
+            const int cf_next = w_next >= 0 ? L.coord[w_next] : 0;
+            int i0, i1, i2;
+            unpack_coord(cf, i0, i1, i2);
+            // what the finishing half reads from DRAM-cold streams: pull it into L2 now
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                prefetch_l2(dvo + ((unsigned)m * (unsigned)G + (unsigned)w));
+                if (coord_eq(cf)) prefetch_l2(co + ((unsigned)m * (unsigned)G + (unsigned)w));
+            }
+            double r[M];
+            gs_pre_elem<D, LdPlain, PITCH>(L, rbuse, Tuse, bo, xo, w, i0, i1, i2, r);
+            if (n == 0) {   // a thread's first point of a step: shared-memory stash (private slot, no sync needed)
+#pragma unroll
+                for (int m = 0; m < M; ++m) st0[m * THREADS] = r[m];
+                st0[(kStashSlots - 1) * THREADS] = __hiloint2double(cf, w);
+            } else {
+                double* sp = st + (size_t)(n - 1) * kStashSlots * nthreads;
+#pragma unroll
+                for (int m = 0; m < M; ++m) sp[(unsigned)(m * nthreads)] = r[m];
+                sp[(unsigned)((kStashSlots - 1) * nthreads)] = __hiloint2double(cf, w);
+            }
+            w = w_next;
+            cf = cf_next;
+            ++n;
+        }
+        return n;
+    };
+
+    first_point(0);
+    int nA = pregather(0);
+#ifdef PDEOP_GS_TIMING
+    const bool dbg = blockIdx.x == 0 && threadIdx.x == 0;
+    long long cA = 0, cB = 0, cW = 0, nP = 0;
+#endif
+    for (int t = 0; t < steps; ++t) {
+#ifdef PDEOP_GS_TIMING
+        const long long c0 = clock64();
+        nP += nA;
+#endif
+        // A half: finish the points of step t
+        if (nA > 0) {
+            double r[M];
+#pragma unroll
+            for (int m = 0; m < M; ++m) r[m] = st0[m * THREADS];
+            const double pk = st0[(kStashSlots - 1) * THREADS];
+            const int w = __double2loint(pk), cf = __double2hiint(pk);
+            int i0, i1, i2;
+            unpack_coord(cf, i0, i1, i2);
+            gs_fin_elem<D, LdPlain, PITCH>(L, rbuse, Tuse, co, dvo, xo, w, i0, i1, i2, coord_eq(cf), r);
+        }
+        for (int n = 1; n < nA; ++n) {
+            const double* sp = st + (size_t)(n - 1) * kStashSlots * nthreads;
+            double r[M];
+#pragma unroll
+            for (int m = 0; m < M; ++m) r[m] = sp[(unsigned)(m * nthreads)];
+            const double pk = sp[(unsigned)((kStashSlots - 1) * nthreads)];
+            const int w = __double2loint(pk), cf = __double2hiint(pk);
+            int i0, i1, i2;
+            unpack_coord(cf, i0, i1, i2);
+            gs_fin_elem<D, LdPlain, PITCH>(L, rbuse, Tuse, co, dvo, xo, w, i0, i1, i2, coord_eq(cf), r);
+        }
+        // release the stores of A(t); the acquire side invalidates L1 (CCTL.IVALL), so the plain loads of the
+        // next halves see what the other CTAs of the cluster wrote
+#ifdef PDEOP_GS_TIMING
+        const long long c1 = clock64();
+#endif
+        if (!SINGLE) cluster_arrive_release();
+        nA = t + 1 < steps ? pregather(t + 1) : 0;
+#ifdef PDEOP_GS_TIMING
+        const long long c2 = clock64();
+#endif
+        if (SINGLE) __syncthreads();
+        else cluster_wait_acquire();
+#ifdef PDEOP_GS_TIMING
+        const long long c3 = clock64();
+        cA += c1 - c0;
+        cB += c2 - c1;
+        cW += c3 - c2;
 #endif
     }
+#ifdef PDEOP_GS_TIMING
+    if (dbg) {
+        g_gs_dbg[0] += steps;
+        g_gs_dbg[1] += cA;
+        g_gs_dbg[2] += cB;
+        g_gs_dbg[3] += cW;
+        g_gs_dbg[4] += nP;
+    }
+#endif
 }
 
 // cross-check variant: one launch per step, no intra-kernel synchronisation
@@ -327,7 +532,7 @@ static int num_sms() {
 
 // tuning switch (read once): PDEOP_GS_SMEM = 0 disables the shared-memory staging of the tables (A/B testing)
 // PDEOP_GS_SINGLE = n: levels whose busiest step has at most n*512 points run with one CTA per instance
-static int g_gs_threads = 0, g_gs_smem = 1, g_gs_single = 0;
+static int g_gs_threads = 0, g_gs_smem = 1, g_gs_single = 0, g_gs_pipe = 1;
 static void gs_tuning() {
     if (g_gs_threads) return;
     g_gs_threads = 512;   // 128 registers/thread; 256/384/1024-thread variants were measured and are not faster
@@ -335,6 +540,38 @@ static void gs_tuning() {
     g_gs_smem = (m && atoi(m) == 0) ? 0 : 1;
     const char* sg = getenv("PDEOP_GS_SINGLE");
     g_gs_single = sg ? atoi(sg) : 0;
+    // PDEOP_GS_PIPE: 0 = unsplit cluster kernel everywhere, 1 = software-pipelined kernel everywhere,
+    // default (2) = pipelined kernel on the latency-bound levels (busiest step <= 3 points per thread), where it
+    // was measured faster (B200: 32x32x32 1.00 vs 1.04 ms, 32x16x16 0.48 vs 0.50 ms per 5 sweeps, batch 32);
+    // on throughput-bound levels (32x64x64: 3.30 vs 3.08 ms) the stash round trip costs more than the overlap gains
+    const char* pp = getenv("PDEOP_GS_PIPE");
+    g_gs_pipe = pp ? atoi(pp) : 2;
+}
+
+// Shrinks the cluster size until all instances' clusters are co-resident (one wave): a cluster needs its CTAs on
+// SMs of one GPC, so e.g. 16 clusters of 8 do not fit a B200 although 128 SMs would suffice (measured: 2 waves,
+// 3.35 ms vs 3.10 ms for 32 clusters of 4 with twice the work).  Results cached per (kernel, smem, cluster size).
+template <class K>
+static void fit_cluster_wave(cudaLaunchConfig_t& cfg, K kern, int B) {
+    static int cache_smem[4] = {-1, -1, -1, -1}, cache_max[4] = {0, 0, 0, 0};   // index log2(cluster size)
+    unsigned& cs = cfg.attrs[0].val.clusterDim.x;
+    while (cs > 1) {
+        int lg = 0;
+        while ((1u << lg) < cs) ++lg;
+        if (cache_smem[lg] != (int)cfg.dynamicSmemBytes) {
+            int nmax = 0;
+            cfg.gridDim = dim3((unsigned)(B * cs));
+            if (cudaOccupancyMaxActiveClusters(&nmax, kern, &cfg) != cudaSuccess) {
+                cudaGetLastError();
+                nmax = B;   // cannot tell: keep the size
+            }
+            cache_smem[lg] = (int)cfg.dynamicSmemBytes;
+            cache_max[lg] = nmax;
+        }
+        if (cache_max[lg] >= B) break;
+        cs /= 2;
+    }
+    cfg.gridDim = dim3((unsigned)(B * cs));
 }
 
 template <int D, int THREADS, int MINB, int PS, bool SINGLE>
@@ -351,12 +588,34 @@ static void launch_gs_inst(cudaLaunchConfig_t& cfg, const LevelDev& L, const dou
         }
     }
     cfg.dynamicSmemBytes = smem;
+    if (!SINGLE) fit_cluster_wave(cfg, kern, (int)(cfg.gridDim.x / cfg.attrs[0].val.clusterDim.x));
     note(cudaLaunchKernelEx(&cfg, kern, L, T, coef, dinv, b, x, nsweeps, done));
+}
+
+template <int D, int THREADS, int PS, bool SINGLE>
+static void launch_gs_pipe(cudaLaunchConfig_t& cfg, const LevelDev& L, const double* T, const double* coef,
+                           const double* dinv, const double* b, double* x, double* stash, size_t stash_stride,
+                           int nsweeps, const int* done) {
+    auto kern = k_gs_pipe<D, THREADS, PS, SINGLE>;
+    size_t smem = (size_t)kStashSlots * THREADS * sizeof(double);
+    if (PS > 0)
+        smem += (size_t)D * kTabEntries * PS * sizeof(double) + ((size_t)(L.S + 8) * L.N[0] + 8 + L.S + 1) * sizeof(int);
+    {
+        static size_t set_for = 0;   // per instantiation
+        if (smem > set_for) {
+            note(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            set_for = smem;
+        }
+    }
+    cfg.dynamicSmemBytes = smem;
+    if (!SINGLE) fit_cluster_wave(cfg, kern, (int)(cfg.gridDim.x / cfg.attrs[0].val.clusterDim.x));
+    note(cudaLaunchKernelEx(&cfg, kern, L, T, coef, dinv, b, x, stash, stash_stride, nsweeps, done));
 }
 
 template <int D>
 static void launch_gs_cluster(cudaStream_t s, const LevelDev& L, int B, const double* T, const double* coef,
-                              const double* dinv, const double* b, double* x, int nsweeps, const int* done) {
+                              const double* dinv, const double* b, double* x, double* stash, size_t stash_stride,
+                              int nsweeps, const int* done) {
     gs_tuning();
     const int threads = g_gs_threads;
     const int per_sm = 1;   // CTAs per SM (register-limited: 128 regs/thread x 512 threads)
@@ -370,7 +629,7 @@ static void launch_gs_cluster(cudaStream_t s, const LevelDev& L, int B, const do
         else if (maxn <= 264 && D <= 2) ps = 264;
         // index tables must fit next to the K tables
         const size_t smem = (size_t)D * kTabEntries * ps * 8 + ((size_t)(L.S + 8) * L.N[0] + 8 + L.S + 1) * 4;
-        if (smem > (size_t)(per_sm == 2 ? 110 : 220) * 1024) ps = 0;
+        if (smem + (size_t)kStashSlots * threads * 8 > (size_t)(per_sm == 2 ? 110 : 220) * 1024) ps = 0;
     }
     // cluster size: as many CTAs per instance as fit on the chip at once, capped by the portable
     // maximum (8) and by the work of one step (largest hyperplane x sweeps in flight)
@@ -406,7 +665,19 @@ static void launch_gs_cluster(cudaStream_t s, const LevelDev& L, int B, const do
         case 264: launch_gs_inst<D, 512, 1, 264, SG>(cfg, L, T, coef, dinv, b, x, nsweeps, done); break; \
         default: launch_gs_inst<D, 512, 1, 0, SG>(cfg, L, T, coef, dinv, b, x, nsweeps, done); break;    \
     }
-    if (single) { PDEOP_GS_DISPATCH(true) } else { PDEOP_GS_DISPATCH(false) }
+#define PDEOP_GS_PIPE_DISPATCH(SG)                                                                                   \
+    switch (ps) {                                                                                                    \
+        case 40: launch_gs_pipe<D, 512, 40, SG>(cfg, L, T, coef, dinv, b, x, stash, stash_stride, nsweeps, done); break;   \
+        case 72: launch_gs_pipe<D, 512, 72, SG>(cfg, L, T, coef, dinv, b, x, stash, stash_stride, nsweeps, done); break;   \
+        case 136: launch_gs_pipe<D, 512, 136, SG>(cfg, L, T, coef, dinv, b, x, stash, stash_stride, nsweeps, done); break; \
+        case 264: launch_gs_pipe<D, 512, 264, SG>(cfg, L, T, coef, dinv, b, x, stash, stash_stride, nsweeps, done); break; \
+        default: launch_gs_pipe<D, 512, 0, SG>(cfg, L, T, coef, dinv, b, x, stash, stash_stride, nsweeps, done); break;    \
+    }
+    const bool use_pipe = stash && (g_gs_pipe == 1 || (g_gs_pipe == 2 && want <= 3 * csize));
+    if (use_pipe) {
+        if (single) { PDEOP_GS_PIPE_DISPATCH(true) } else { PDEOP_GS_PIPE_DISPATCH(false) }
+    } else if (single) { PDEOP_GS_DISPATCH(true) } else { PDEOP_GS_DISPATCH(false) }
+#undef PDEOP_GS_PIPE_DISPATCH
 #undef PDEOP_GS_DISPATCH
 }
 
@@ -429,13 +700,13 @@ void be_dinv(stream_t st, const LevelDev& L, int B, const double* T, const doubl
 }
 
 void be_gs(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, const double* dinv,
-           const double* b, double* x, int nsweeps, const int* done, int variant) {
+           const double* b, double* x, double* stash, size_t stash_stride, int nsweeps, const int* done, int variant) {
     if (nsweeps <= 0) return;
     cudaStream_t s = (cudaStream_t)st;
     if (variant == 0) {
-        if (L.D == 1) launch_gs_cluster<1>(s, L, B, T, coef, dinv, b, x, nsweeps, done);
-        else if (L.D == 2) launch_gs_cluster<2>(s, L, B, T, coef, dinv, b, x, nsweeps, done);
-        else launch_gs_cluster<3>(s, L, B, T, coef, dinv, b, x, nsweeps, done);
+        if (L.D == 1) launch_gs_cluster<1>(s, L, B, T, coef, dinv, b, x, stash, stash_stride, nsweeps, done);
+        else if (L.D == 2) launch_gs_cluster<2>(s, L, B, T, coef, dinv, b, x, stash, stash_stride, nsweeps, done);
+        else launch_gs_cluster<3>(s, L, B, T, coef, dinv, b, x, stash, stash_stride, nsweeps, done);
         PDEOP_COUNT(1);
         PDEOP_LAUNCH_CHECK();
         return;

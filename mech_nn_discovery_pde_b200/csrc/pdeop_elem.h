@@ -156,20 +156,6 @@ PDEOP_HD const double* axis_table(const double* T, int a) { return T + a * (kTab
 // ------------------------------------------------------------------------------------------------
 // PITCH: table pitch (kTabPitch for tables in global memory, a smaller compile-time pitch for the copy the
 // Gauss-Seidel kernel stages in shared memory); rowbase: L.rowbase or its shared-memory copy.
-#if defined(PDEOP_GS_TIMING) && defined(__CUDA_ARCH__)
-extern __device__ unsigned long long g_gs_dbg[8];
-#define PDEOP_TSTAMP(k)                                                       \
-    if (blockIdx.x == 0 && threadIdx.x == 0) {                                \
-        const long long now_ = clock64();                                    \
-        g_gs_dbg[k] += (unsigned long long)(now_ - tprev_);                   \
-        tprev_ = now_;                                                        \
-    }
-#define PDEOP_TSTART() long long tprev_ = clock64()
-#else
-#define PDEOP_TSTAMP(k)
-#define PDEOP_TSTART()
-#endif
-
 // keeps the compiler from sinking a batch of loads down to their first use (device only)
 #if defined(__CUDA_ARCH__)
 #define PDEOP_LOAD_FENCE() asm volatile("" ::: "memory")
@@ -177,69 +163,180 @@ extern __device__ unsigned long long g_gs_dbg[8];
 #define PDEOP_LOAD_FENCE()
 #endif
 
-template <int D, class LD, int PITCH>
-PDEOP_HD void k_neighbors(const LevelDev& L, const int* __restrict__ rowbase, const double* __restrict__ T,
-                          const double* x, int i0, int i1, int i2, double acc[1 + 2 * D]) {
-    const int G = L.G, N0 = L.N[0];
-    const int idx[3] = {i0, i1, i2};
-    // rb[o*N0] = rowbase[s+o][i0],  rb[o*N0 + o] = rowbase[s+o][i0+o]
-    const int* __restrict__ rb = rowbase + (i0 + i1 + i2 + 4) * N0 + i0;
+// Clamp a (possibly out-of-range or negative) wave index into [0, G).  An out-of-range neighbour is only ever
+// multiplied by an exact-zero table entry, so its value is irrelevant as long as the address is valid and the
+// value finite: one unsigned minimum replaces the bounds predicates, zero fills and 64-bit sign extensions.
+PDEOP_HD unsigned clamp_wave(int w, unsigned gm1) {
+    const unsigned u = (unsigned)w;
+    return u < gm1 ? u : gm1;
+}
+
+// wave index (unclamped) of the neighbour at offset o along internal axis ax; rb = rowbase + (s+4)*N0 + i0
+PDEOP_HD int neighbor_wave(const int* __restrict__ rb, int ax, int N0, int i1, int o) {
+    if (ax == 2) return rb[o * N0] + i1;          // row (s+o, i0)
+    if (ax == 1) return rb[o * N0] + i1 + o;      // row (s+o, i0), column i1+o
+    return rb[o * N0 + o] + i1;                   // row (s+o, i0+o)
+}
+
+// Neighbour values of one axis (offsets o = -4..-1, 1..4 at j = 0..7).
+struct AxisNb {
+    double un[8], pn[8], qn[8];
+};
+
+// Structural zeros of K along an axis of extent n (lp_pde_central_diff.py:1000-1006): a derivative row reaches 3
+// or 4 positions away only through the one-sided stencils of the two positions next to either end.  Hence, for
+// |o| >= 3:  K[u_c/u_cc(i), u(i+o)] = 0 unless i is such an end position      (axis_end1)
+//            K[u(i), u_c/u_cc(i+o)] = 0 unless i+o is                         (axis_end3: i in 3..5 or n-6..n-4)
+// Pure index tests: the skipped terms are exact zeros.
+PDEOP_HD bool axis_end1(int i, int n) { return i <= 1 || i >= n - 2; }
+PDEOP_HD bool axis_end3(int i, int n) { return (i >= 3 && i <= 5) || (i >= n - 6 && i <= n - 4); }
+
+// Issue the loads of one axis.  SPLIT: without the backward distance-1 neighbour (o = -1), see k_gather.
+template <int D, class LD, bool SPLIT>
+PDEOP_HD void gather_axis_load(const LevelDev& L, const int* __restrict__ rb, const double* x, int a, int i, int i1,
+                               AxisNb& nb) {
+    const unsigned G = (unsigned)L.G, gm1 = G - 1u;
+    const int ax = 3 - D + a;
+    const int n = L.N[ax], N0 = L.N[0];
+    const unsigned gp = (unsigned)(1 + a) * G, gq = (unsigned)(1 + D + a) * G;   // plane offsets (M*G < 2^31)
+    const bool e3 = axis_end3(i, n);
 #pragma unroll
-    for (int m = 0; m < 1 + 2 * D; ++m) acc[m] = 0.0;
+    for (int j = 0; j < 8; ++j) {
+        const int o = j < 4 ? j - 4 : j - 3;
+        if (SPLIT && o == -1) continue;
+        const unsigned wn = clamp_wave(neighbor_wave(rb, ax, N0, i1, o), gm1);
+        nb.un[j] = LD::ld(x + wn);
+        if (o >= -2 && o <= 2) {
+            nb.pn[j] = LD::ld(x + (wn + gp));
+            nb.qn[j] = LD::ld(x + (wn + gq));
+        } else {
+            nb.pn[j] = e3 ? LD::ld(x + (wn + gp)) : 0.0;
+            nb.qn[j] = e3 ? LD::ld(x + (wn + gq)) : 0.0;
+        }
+    }
+}
+
+// Canonical FMA order per axis (every kernel that inlines this body, and the host emulator, produce the same bits):
+//   near offsets o = -2,-1,1,2 : au += UU u, au += UPn p, au += UQn q, ap += UP u, aq += UQ u
+//   far u terms  o = -4,-3,3,4 : au += UU u
+//   if axis_end1(i), far       : ap += UP u, aq += UQ u
+//   if axis_end3(i), far       : au += UPn p, au += UQn q
+template <int D, int PITCH, bool SPLIT>
+PDEOP_HD void gather_axis_fma(const LevelDev& L, const double* __restrict__ T, int a, int i, const AxisNb& nb,
+                              double acc[1 + 2 * D]) {
+    const int n = L.N[3 - D + a];
+    const double* __restrict__ Ta = axis_table<PITCH>(T, a) + (i + kTabPad);
+    double au = 0.0, ap = 0.0, aq = 0.0;
+#pragma unroll
+    for (int j = 2; j < 6; ++j) {
+        const int o = j < 4 ? j - 4 : j - 3;
+        if (SPLIT && o == -1) continue;
+        au = fma(Ta[(T_UU + o + 4) * PITCH], nb.un[j], au);
+        au = fma(Ta[(T_UP - o + 4) * PITCH + o], nb.pn[j], au);
+        au = fma(Ta[(T_UQ - o + 4) * PITCH + o], nb.qn[j], au);
+        ap = fma(Ta[(T_UP + o + 4) * PITCH], nb.un[j], ap);
+        aq = fma(Ta[(T_UQ + o + 4) * PITCH], nb.un[j], aq);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int o = j < 4 ? j - 4 : j - 3;
+        if (o >= -2 && o <= 2) continue;
+        au = fma(Ta[(T_UU + o + 4) * PITCH], nb.un[j], au);
+    }
+    if (axis_end1(i, n)) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int o = j < 4 ? j - 4 : j - 3;
+            if (o >= -2 && o <= 2) continue;
+            ap = fma(Ta[(T_UP + o + 4) * PITCH], nb.un[j], ap);
+            aq = fma(Ta[(T_UQ + o + 4) * PITCH], nb.un[j], aq);
+        }
+    }
+    if (axis_end3(i, n)) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int o = j < 4 ? j - 4 : j - 3;
+            if (o >= -2 && o <= 2) continue;
+            au = fma(Ta[(T_UP - o + 4) * PITCH + o], nb.pn[j], au);
+            au = fma(Ta[(T_UQ - o + 4) * PITCH + o], nb.qn[j], au);
+        }
+    }
+    acc[0] += au;
+    acc[1 + a] += ap;
+    acc[1 + D + a] += aq;
+}
+
+// acc[m] = sum over OFF-POINT couplings  K[(g,m),(g',m')] x[g',m'],  g' = g + o e_a.
+// SPLIT = false: all offsets o in [-4,4] \ {0}.
+// SPLIT = true : all but the backward distance-1 neighbours (o = -1), which gs_back1 adds.  Under wavefront
+//   Gauss-Seidel those are the only values written in the immediately preceding step, so everything gathered
+//   here can be done one step ahead, off the critical path of the sweep.
+// The loads of axis a+1 are issued before the FMAs of axis a (at most two axes in flight): the kernels built on
+// this body are bound by dependent memory round trips, not by bandwidth.
+// BSUB: also loads b (issued with the last axis batch, when the registers of the first axes are free again) and
+// returns acc[m] = b[m] - sum instead of the sum.
+template <int D, class LD, int PITCH, bool SPLIT, bool BSUB>
+PDEOP_HD void k_gather(const LevelDev& L, const int* __restrict__ rowbase, const double* __restrict__ T,
+                       const double* x, const double* __restrict__ b, unsigned w, int i0, int i1, int i2,
+                       double acc[1 + 2 * D]) {
+    constexpr int M = 1 + 2 * D;
+    const int idx[3] = {i0, i1, i2};
+    const int* __restrict__ rb = rowbase + (i0 + i1 + i2 + 4) * L.N[0] + i0;
+#pragma unroll
+    for (int m = 0; m < M; ++m) acc[m] = 0.0;
+    AxisNb nb[D];
+    double bl[M];
+    gather_axis_load<D, LD, SPLIT>(L, rb, x, 0, idx[3 - D], i1, nb[0]);
 #pragma unroll
     for (int a = 0; a < D; ++a) {
-        const int ax = 3 - D + a;
-        const int n = L.N[ax];
-        const int i = idx[ax];
-        const double* __restrict__ Ta = axis_table<PITCH>(T, a) + (i + kTabPad);
-        const double* xu = x;
-        const double* xp = x + (1 + a) * G;
-        const double* xq = x + (1 + D + a) * G;
-        // phase 1: all 24 neighbour loads of this axis in flight together (one memory round trip per axis
-        // instead of one per neighbour: the kernels built on this body are latency-bound, not bandwidth-bound).
-        // Batching all axes at once (needs >200 registers, 256-thread CTAs) was measured and is not faster.
-        // Structural zeros: a derivative row reaches 3 or 4 positions away only through the one-sided stencils
-        // of the two positions next to either end (lp_pde_central_diff.py:1000-1006).  So for |o| >= 3 the
-        // couplings u(i) <-> u_c/u_cc(i+o) vanish unless position i+o is such an end position, and
-        // u_c/u_cc(i) <-> u(i+o) vanish unless i is.  Pure index tests: the skipped terms are exact zeros.
-        const bool i_end = i <= 1 || i >= n - 2;
-        double un[8], pn[8], qn[8];
+        if (a + 1 < D) gather_axis_load<D, LD, SPLIT>(L, rb, x, a + 1, idx[3 - D + a + 1], i1, nb[a + 1]);
+        if (BSUB && a == D - 1) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int o = j < 4 ? j - 4 : j - 3;
-            const int ii = i + o;
-            const bool ok = (unsigned)ii < (unsigned)n;
-            const bool far = o < -2 || o > 2;
-            const bool okpq = ok && (!far || ii <= 1 || ii >= n - 2);
-            int wn;
-            if (ax == 2) wn = rb[o * N0] + i1;
-            else if (ax == 1) wn = rb[o * N0] + i1 + o;
-            else wn = rb[o * N0 + o] + i1;
-            un[j] = ok ? LD::ld(xu + wn) : 0.0;
-            pn[j] = okpq ? LD::ld(xp + wn) : 0.0;
-            qn[j] = okpq ? LD::ld(xq + wn) : 0.0;
+            for (int m = 0; m < M; ++m) bl[m] = b[(unsigned)m * (unsigned)L.G + w];
         }
         PDEOP_LOAD_FENCE();
-        // phase 2: explicit fma => the same bits from every kernel that inlines this body and from the emulator
-        double au = 0.0, ap = 0.0, aq = 0.0;
+        gather_axis_fma<D, PITCH, SPLIT>(L, T, a, idx[3 - D + a], nb[a], acc);
+    }
+    if (BSUB) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int o = j < 4 ? j - 4 : j - 3;
-            const int ii = i + o;
-            const bool far = o < -2 || o > 2;
-            au = fma(Ta[(T_UU + o + 4) * PITCH], un[j], au);
-            if (!far || ii <= 1 || ii >= n - 2) {
-                au = fma(Ta[(T_UP - o + 4) * PITCH + o], pn[j], au);
-                au = fma(Ta[(T_UQ - o + 4) * PITCH + o], qn[j], au);
-            }
-            if (!far || i_end) {
-                ap = fma(Ta[(T_UP + o + 4) * PITCH], un[j], ap);
-                aq = fma(Ta[(T_UQ + o + 4) * PITCH], un[j], aq);
-            }
-        }
-        acc[0] += au;
-        acc[1 + a] += ap;
-        acc[1 + D + a] += aq;
+        for (int m = 0; m < M; ++m) acc[m] = bl[m] - acc[m];
+    }
+}
+
+// Backward distance-1 neighbours (o = -1 along every active axis): loads, then r[m] -= K[m, neighbour] x[neighbour].
+// Split in two so that a caller can put these loads in flight together with its other loads.
+template <int D>
+struct Back1 {
+    double un[D], pn[D], qn[D];
+};
+
+template <int D, class LD>
+PDEOP_HD void gs_back1_load(const LevelDev& L, const int* __restrict__ rowbase, const double* x, int i0, int i1, int i2,
+                            Back1<D>& nb) {
+    const unsigned G = (unsigned)L.G, gm1 = G - 1u;
+    const int N0 = L.N[0];
+    const int* __restrict__ rb = rowbase + (i0 + i1 + i2 + 4) * N0 + i0;
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+        const unsigned wn = clamp_wave(neighbor_wave(rb, 3 - D + a, N0, i1, -1), gm1);
+        nb.un[a] = LD::ld(x + wn);
+        nb.pn[a] = LD::ld(x + (wn + (unsigned)(1 + a) * G));
+        nb.qn[a] = LD::ld(x + (wn + (unsigned)(1 + D + a) * G));
+    }
+}
+
+template <int D, int PITCH>
+PDEOP_HD void gs_back1_apply(const double* __restrict__ T, int i0, int i1, int i2, const Back1<D>& nb,
+                             double r[1 + 2 * D]) {
+    const int idx[3] = {i0, i1, i2};
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+        const double* __restrict__ Ta = axis_table<PITCH>(T, a) + (idx[3 - D + a] + kTabPad);
+        r[0] = fma(-Ta[(T_UU + 3) * PITCH], nb.un[a], r[0]);
+        r[0] = fma(-Ta[(T_UP + 5) * PITCH - 1], nb.pn[a], r[0]);
+        r[0] = fma(-Ta[(T_UQ + 5) * PITCH - 1], nb.qn[a], r[0]);
+        r[1 + a] = fma(-Ta[(T_UP + 3) * PITCH], nb.un[a], r[1 + a]);
+        r[1 + D + a] = fma(-Ta[(T_UQ + 3) * PITCH], nb.un[a], r[1 + D + a]);
     }
 }
 
@@ -315,7 +412,7 @@ PDEOP_HD void apply_k_elem(const LevelDev& L, const double* __restrict__ T, cons
     unpack_coord(L.coord[w], i0, i1, i2);
     const int flags = L.flags[w];
     double acc[M];
-    k_neighbors<D, LdPlain, kTabPitch>(L, L.rowbase, T, x, i0, i1, i2, acc);
+    k_gather<D, LdPlain, kTabPitch, false, false>(L, L.rowbase, T, x, nullptr, 0u, i0, i1, i2, acc);
     PointLocal<D> pl;
     load_local<D>(L, T, coef, w, i0, i1, i2, flags, pl);
     double xl[M];
@@ -344,34 +441,37 @@ PDEOP_HD void apply_k_elem(const LevelDev& L, const double* __restrict__ T, cons
 
 // One lexicographic Gauss-Seidel update of the M unknowns of point w (channel order 0..M-1):
 //   x_j <- (b_j - sum_{k != j} K_jk x_k) / K_jj   with already-updated values for k < j.
+// Split in two halves so that the wavefront kernel can run the first one a step ahead:
+//   gs_pre_elem : r[m] = b[m] - (all off-point couplings except the backward distance-1 neighbours)
+//   gs_fin_elem : own-point loads and the backward distance-1 loads in one batch, r -= those couplings, then the
+//                 sequential channel solve and the store.
 // The equation-row part of the point block is rank one (c c^T): the running sum S = c.x is kept up to
 // date as channels are updated, and the division is a multiplication by the precomputed reciprocal diagonal.
 template <int D, class LD, int PITCH>
-PDEOP_HD void gs_elem(const LevelDev& L, const int* __restrict__ rowbase, const double* __restrict__ T,
-                      const double* __restrict__ coef, const double* __restrict__ dinv,
-                      const double* __restrict__ b, double* x, int w) {
+PDEOP_HD void gs_pre_elem(const LevelDev& L, const int* __restrict__ rowbase, const double* __restrict__ T,
+                          const double* __restrict__ b, const double* x, int w, int i0, int i1, int i2,
+                          double r[1 + 2 * D]) {
+    k_gather<D, LD, PITCH, true, true>(L, rowbase, T, x, b, (unsigned)w, i0, i1, i2, r);
+}
+
+template <int D, class LD, int PITCH>
+PDEOP_HD void gs_fin_elem(const LevelDev& L, const int* __restrict__ rowbase, const double* __restrict__ T,
+                          const double* __restrict__ coef, const double* __restrict__ dinv, double* x, int w, int i0,
+                          int i1, int i2, bool eq, double r[1 + 2 * D]) {
     constexpr int M = 1 + 2 * D;
-    const int G = L.G;
-    PDEOP_TSTART();
-    int i0, i1, i2;
-    unpack_coord(L.coord[w], i0, i1, i2);
-    const bool eq = L.flags[w] & 1;
-    if (eq && i0 < 0) return;   // (keeps the flag load before the timestamp)
-    PDEOP_TSTAMP(4);
-    // own-point loads first: their latency overlaps the neighbour gathers
-    double xl[M], c[M], bl[M], di[M];
+    const unsigned G = (unsigned)L.G, uw = (unsigned)w;
+    // one batch of loads: old own-point values, equation coefficients, reciprocal diagonals, backward neighbours
+    double xl[M], c[M], di[M];
+    Back1<D> nb;
+    gs_back1_load<D, LD>(L, rowbase, x, i0, i1, i2, nb);
 #pragma unroll
     for (int m = 0; m < M; ++m) {
-        xl[m] = LD::ld(x + m * G + w);
-        c[m] = eq ? coef[m * G + w] : 0.0;
-        bl[m] = b[m * G + w];
-        di[m] = dinv[m * G + w];
+        xl[m] = LD::ld(x + ((unsigned)m * G + uw));
+        c[m] = eq ? coef[(unsigned)m * G + uw] : 0.0;
+        di[m] = dinv[(unsigned)m * G + uw];
     }
     PDEOP_LOAD_FENCE();
-    double acc[M];
-    k_neighbors<D, LD, PITCH>(L, rowbase, T, x, i0, i1, i2, acc);
-    if (acc[0] == 1.2345e300) return;   // (forces the gather results before the timestamp)
-    PDEOP_TSTAMP(5);
+    gs_back1_apply<D, PITCH>(T, i0, i1, i2, nb, r);
     PointLocal<D> pl;
     load_axis_local<D, PITCH>(T, i0, i1, i2, pl);
     // Canonical arithmetic (every kernel that inlines this body, and the host emulator, produce the same bits):
@@ -379,8 +479,6 @@ PDEOP_HD void gs_elem(const LevelDev& L, const int* __restrict__ rowbase, const 
     //   u   : off = c_u t + l_0 + l_1 + ...,   l_a = fma(uq_a, x_qa, up_a x_pa)
     //   p_a : off = fma(pq_a, x_qa, fma(up_a, x_u, c_pa t));   q_a : off = fma(pq_a, x_pa, fma(uq_a, x_u, c_qa t))
     //   with t = fma(-c_m, x_m, S),  x_m <- (r_m - off) * dinv_m,  S <- fma(c_m, x_m, t)
-#pragma unroll
-    for (int m = 0; m < M; ++m) acc[m] = bl[m] - acc[m];
     double S = c[0] * xl[0];
 #pragma unroll
     for (int a = 0; a < D; ++a) S = S + fma(c[1 + D + a], xl[1 + D + a], c[1 + a] * xl[1 + a]);
@@ -389,7 +487,7 @@ PDEOP_HD void gs_elem(const LevelDev& L, const int* __restrict__ rowbase, const 
         double off = c[0] * t;
 #pragma unroll
         for (int a = 0; a < D; ++a) off = off + fma(pl.uq[a], xl[1 + D + a], pl.up[a] * xl[1 + a]);
-        const double xn = (acc[0] - off) * di[0];
+        const double xn = (r[0] - off) * di[0];
         S = fma(c[0], xn, t);
         xl[0] = xn;
     }
@@ -398,7 +496,7 @@ PDEOP_HD void gs_elem(const LevelDev& L, const int* __restrict__ rowbase, const 
         const int m = 1 + a;
         const double t = fma(-c[m], xl[m], S);
         const double off = fma(pl.pq[a], xl[1 + D + a], fma(pl.up[a], xl[0], c[m] * t));
-        const double xn = (acc[m] - off) * di[m];
+        const double xn = (r[m] - off) * di[m];
         S = fma(c[m], xn, t);
         xl[m] = xn;
     }
@@ -407,13 +505,25 @@ PDEOP_HD void gs_elem(const LevelDev& L, const int* __restrict__ rowbase, const 
         const int m = 1 + D + a;
         const double t = fma(-c[m], xl[m], S);
         const double off = fma(pl.pq[a], xl[1 + a], fma(pl.uq[a], xl[0], c[m] * t));
-        const double xn = (acc[m] - off) * di[m];
+        const double xn = (r[m] - off) * di[m];
         S = fma(c[m], xn, t);
         xl[m] = xn;
     }
 #pragma unroll
-    for (int m = 0; m < M; ++m) x[m * G + w] = xl[m];
-    PDEOP_TSTAMP(6);
+    for (int m = 0; m < M; ++m) x[(unsigned)m * G + uw] = xl[m];
+}
+
+// both halves back to back (the one-launch-per-step cross-check kernel and the host emulator)
+template <int D, class LD, int PITCH>
+PDEOP_HD void gs_elem(const LevelDev& L, const int* __restrict__ rowbase, const double* __restrict__ T,
+                      const double* __restrict__ coef, const double* __restrict__ dinv,
+                      const double* __restrict__ b, double* x, int w) {
+    int i0, i1, i2;
+    const int cf = L.coord[w];
+    unpack_coord(cf, i0, i1, i2);
+    double r[1 + 2 * D];
+    gs_pre_elem<D, LD, PITCH>(L, rowbase, T, b, x, w, i0, i1, i2, r);
+    gs_fin_elem<D, LD, PITCH>(L, rowbase, T, coef, dinv, x, w, i0, i1, i2, coord_eq(cf), r);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -146,6 +146,7 @@ static int build_level(pdeop_plan* pl, LevelHost& lh, const int* dims, int n_iv,
         }
         if (eq) {
             flags[ww] |= 1;
+            coord[ww] |= 1 << 30;
             ++n_eq;
         }
     }
@@ -254,7 +255,8 @@ extern "C" void pdeop_plan_destroy(pdeop_plan* pl) {
 // scratch layout (doubles): [state | atb | x | w | V[restart] | Z[restart] | per level>=1: x,b,r | cwork]
 struct Scratch {
     FgmresState* state;
-    double *atb, *x, *w, *V, *Z, *cwork;
+    double *atb, *x, *w, *V, *Z, *cwork, *gs_stash;
+    size_t gs_stash_stride;
     std::vector<double*> lx, lb, lr;
     size_t n0;
 };
@@ -267,6 +269,7 @@ static size_t scratch_doubles(const pdeop_plan* pl, int restart) {
     size_t tot = state_doubles() + n0 * (3 + 2 * (size_t)std::max(restart, 1));
     for (int l = 1; l < pl->n_grid; ++l) tot += 3 * (size_t)pl->B * pl->lev[l].dev.M * pl->lev[l].dev.G;
     tot += 2 * (size_t)pl->B * pl->nc;
+    tot += (size_t)pl->B * be_gs_stash_doubles(L0);
     return tot;
 }
 
@@ -291,7 +294,9 @@ static Scratch carve(const pdeop_plan* pl, void* scratch, int restart) {
         s.lb[l] = p; p += nl;
         s.lr[l] = p; p += nl;
     }
-    s.cwork = p;
+    s.cwork = p; p += 2 * (size_t)pl->B * pl->nc;
+    s.gs_stash = p;
+    s.gs_stash_stride = be_gs_stash_doubles(L0);
     return s;
 }
 
@@ -369,7 +374,8 @@ static void vcycle(pdeop_plan* pl, const pdeop_solver_cfg* cfg, void* persist, S
     const int* done = &sc.state->done;
     {
         ProfScope ps(l == 0 ? PC_GS_FINE : PC_GS_COARSE, st);
-        be_gs(st, L, B, P_T(pl, persist, l), P_coef(pl, persist, l), P_dinv(pl, persist, l), b, x, cfg->gs_pre, done,
+        be_gs(st, L, B, P_T(pl, persist, l), P_coef(pl, persist, l), P_dinv(pl, persist, l), b, x, sc.gs_stash, sc.gs_stash_stride,
+              cfg->gs_pre, done,
               cfg->gs_variant);
     }
     {
@@ -393,7 +399,8 @@ static void vcycle(pdeop_plan* pl, const pdeop_solver_cfg* cfg, void* persist, S
         be_interp(st, Lc, L, B, L.M, sc.lx[l + 1], x, 1, done);
     }
     ProfScope ps(l == 0 ? PC_GS_FINE : PC_GS_COARSE, st);
-    be_gs(st, L, B, P_T(pl, persist, l), P_coef(pl, persist, l), P_dinv(pl, persist, l), b, x, cfg->gs_post, done,
+    be_gs(st, L, B, P_T(pl, persist, l), P_coef(pl, persist, l), P_dinv(pl, persist, l), b, x, sc.gs_stash, sc.gs_stash_stride,
+          cfg->gs_post, done,
           cfg->gs_variant);
 }
 
@@ -580,7 +587,7 @@ extern "C" int pdeop_stage(pdeop_plan* pl, const pdeop_solver_cfg* cfg, int stag
             be_pack(stream, L, B, in1, t1);
             be_pack(stream, L, B, in2, t2);
             be_gs(stream, L, B, P_T(pl, persist, level), P_coef(pl, persist, level), P_dinv(pl, persist, level), t1, t2,
-                  count, nullptr, cfg->gs_variant);
+                  sc.gs_stash, sc.gs_stash_stride, count, nullptr, cfg->gs_variant);
             be_unpack(stream, L, B, t2, out);
             break;
         case PDEOP_STAGE_RESTRICT: {

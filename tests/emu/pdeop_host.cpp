@@ -106,7 +106,7 @@ static void gs_t(const LevelDev& L, int B, const double* T, const double* coef, 
 }
 
 void be_gs(stream_t, const LevelDev& L, int B, const double* T, const double* coef, const double* dinv,
-           const double* b, double* x, int nsweeps, const int* done, int) {
+           const double* b, double* x, double*, size_t, int nsweeps, const int* done, int) {
     if (done && *done) return;
     if (nsweeps <= 0) return;
     if (L.D == 1) gs_t<1>(L, B, T, coef, dinv, b, x, nsweeps);

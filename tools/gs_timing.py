@@ -36,9 +36,6 @@ for dims, n_grid in (((32, 64, 64), 4), ((32, 32, 32), 3), ((32, 16, 16), 2)):
     for _ in range(reps): call()
     e1.record(); torch.cuda.synchronize()
     lib.dll.pdeop_gs_dbg_read(buf)
-    st, cc, cb, npt = [int(buf[i]) for i in range(4)]
-    ph = [int(buf[i]) for i in range(4, 7)]
-    print("   per point update: coord/flags %.0f | gather (own loads + 3 axis batches + fma) %.0f | channel solve + stores %.0f cycles"
-          % tuple(p / max(npt, 1) for p in ph))
-    print(f"dims {dims}: {e0.elapsed_time(e1)/reps:.3f} ms/call | thread0: steps {st//reps}, point updates {npt//reps}, "
-          f"cycles/step compute {cc/st:.0f} barrier {cb/st:.0f}, cycles per point update {cc/max(npt,1):.0f}")
+    st, cA, cB, cW, npt = [int(buf[i]) for i in range(5)]
+    print(f"dims {dims}: {e0.elapsed_time(e1)/reps:.3f} ms/call | thread0 per step: A {cA/st:.0f}  B {cB/st:.0f}  wait {cW/st:.0f} cycles; "
+          f"steps {st//reps}, point updates per step {npt/st:.2f}")
