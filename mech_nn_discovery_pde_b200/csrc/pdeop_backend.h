@@ -46,10 +46,37 @@ inline size_t be_gs_stash_doubles(const LevelDev& L) { return 8 * ((size_t)L.G +
 // dinv[m][w] = 1 / K[(w,m),(w,m)]: reciprocal diagonal of K, computed once per operator set-up
 void be_dinv(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, double* dinv);
 void be_dense(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, double* Kd);
+// ---- dense coarsest level: storage of the factor's inverse diagonal blocks and (chain solver) scaled band ----
+// Linv area (doubles): [inverse diagonal blocks | their transposes | pad | Wc | WTc], see be_cholesky.
+// The chain solver (persistent cluster kernel, pdeop_cuda.cu) needs 16-byte aligned rows: n even, and at least four
+// block rows to be worth it.
+struct ChainLayout {
+    int use;       // 1: chain solver applies to (n, bw)
+    int nblk;      // block rows of kSolveBlk
+    int pw;        // Wc row pitch  = band columns per row, rounded up to 32
+    int nbmax;     // block columns a block row's band touches
+    int pwt;       // WTc row pitch = nbmax * kSolveBlk
+};
+inline ChainLayout be_chain_layout(int n, int bw) {
+    ChainLayout c;
+    c.nblk = (n + kSolveBlk - 1) / kSolveBlk;
+    c.pw = (bw + 31) & ~31;
+    c.nbmax = (c.pw + kSolveBlk - 1) / kSolveBlk;
+    c.pwt = c.nbmax * kSolveBlk;
+    c.use = (n % 2 == 0) && c.nblk >= 8 && c.nbmax + 1 <= 32;   // vector window of nbmax+1 blocks must fit shared memory
+    return c;
+}
+inline size_t be_chol_linv_doubles(int B, int n, int bw) {
+    const ChainLayout c = be_chain_layout(n, bw);
+    size_t tot = 2 * (size_t)B * c.nblk * kSolveBlk * kSolveBlk;
+    if (c.use) tot += 64 + (size_t)B * n * ((size_t)c.pw + c.pwt);
+    return tot;
+}
+
 // in-place lower Cholesky of B dense n x n matrices; state->chol_info set on a non-positive pivot
 // (bw = half-bandwidth of the matrix in the dense ordering; nothing outside the band is touched)
-// Linv: 2 * B * ceil(n/kSolveBlk) * kSolveBlk^2 doubles receiving the inverses of the diagonal blocks of L and,
-// after them, their transposes
+// Linv: be_chol_linv_doubles(B, n, bw) doubles receiving the inverses of the diagonal blocks of L, their transposes
+// and, when the chain solver applies, the block-scaled band W = blockdiag(L_kk)^-1 L in two compact layouts
 void be_cholesky(stream_t st, int B, int n, int bw, double* Kd, double* Linv, FgmresState* state);
 // out = (L L^T)^-1 rhs for the dense system of level L (n = M*G); rhs/out in wave/planar layout, the
 // factor in band ordering; work: 2*B*n doubles

@@ -30,7 +30,10 @@ constexpr int kTabPitch = 1032;
 // the farthest forward neighbour (s+1+4) was then finished by the previous sweep in step t-1, not in step t.
 constexpr int kGsLag = 6;
 constexpr int kMaxRestart = 32;
-constexpr int kSolveBlk = 256;    // block size of the dense triangular solves (inverse diagonal blocks)
+// Block size of the dense triangular solves (inverse diagonal blocks).  128: the chain solver prefetches, per CTA,
+// the previous block's columns of its rows (kSolveBlk/4 rows x kSolveBlk columns) into shared memory; at 128 that
+// buffer is 32 KB and leaves >160 KB for the TMA stages that keep HBM busy, at 256 it would take 128 KB.
+constexpr int kSolveBlk = 128;
 
 enum TabIdx { T_UU = 0, T_UP = 9, T_UQ = 18, T_PP = 27, T_QQ = 28, T_PQ = 29 };
 

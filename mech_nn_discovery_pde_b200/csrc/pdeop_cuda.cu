@@ -1213,6 +1213,79 @@ __global__ void __launch_bounds__(kSolveBlk) k_trtri(int n, const double* __rest
     for (int i = 0; i < kSolveBlk; ++i) It[(size_t)j * kSolveBlk + i] = Ib[(size_t)i * kSolveBlk + j];
 }
 
+// =================================================================================================
+// Chain solver, set-up half.  W = blockdiag(L_kk)^-1 L restricted to the band: with it
+//     L^-1 = Wt^-1 D^-1   and   L^-T = D^-T Wt^-T     (D = blockdiag(L_kk), Wt = W with identity diagonal blocks),
+// so both triangular solves become a chain of pure band GEMVs (no triangular block solve between two chain
+// steps) framed by two batched block-diagonal products that are off the chain's critical path.
+// W is stored twice, compactly (the n x n factor array keeps only the band, 1/8 of its bytes at n = 14336):
+//   Wc [ib][r][pw]  : row r of block row k holds columns c_lo(k) .. k0-1,  c_lo(k) = max(0, k0 - pw)
+//   WTc[ib][c][pwt] : row c of block column k holds rows (k+1)*256 .. of W[., c]  (zero where W stores nothing)
+// so that the forward chain streams rows of Wc and the backward chain rows of WTc with the same kernel.
+// One CTA: block row k, a tile of 32 band columns; thread i owns row i of the block, 32 accumulators.
+// =================================================================================================
+constexpr int kWTile = 32;
+__global__ void __launch_bounds__(kSolveBlk) k_make_w(int n, int nblk, int pw, int pwt, const double* __restrict__ Lf,
+                                                      size_t strideL, const double* __restrict__ LinvT,
+                                                      double* __restrict__ Wc, double* __restrict__ WTc) {
+    extern __shared__ __align__(16) double mw_p[];   // [kSolveBlk][kWTile]
+    const int k = blockIdx.y + 1, ib = blockIdx.z;
+    const int k0 = k * kSolveBlk;
+    const int w = k0 + kSolveBlk < n ? kSolveBlk : n - k0;
+    const int c_lo = k0 - pw > 0 ? k0 - pw : 0;
+    const int ct0 = c_lo + blockIdx.x * kWTile;
+    if (ct0 >= k0) return;
+    const double* Lb = Lf + (size_t)ib * strideL;
+    for (int idx = threadIdx.x; idx < kSolveBlk * kWTile; idx += blockDim.x) {
+        const int j = idx / kWTile, c = idx % kWTile;
+        mw_p[idx] = j < w ? Lb[(size_t)(k0 + j) * n + ct0 + c] : 0.0;
+    }
+    __syncthreads();
+    const int i = threadIdx.x;
+    const double* It = LinvT + ((size_t)ib * nblk + k) * kSolveBlk * kSolveBlk;   // It[j][i] = inv(L_kk)[i][j]
+    double acc[kWTile];
+#pragma unroll
+    for (int c = 0; c < kWTile; ++c) acc[c] = 0.0;
+    const int jmax = i | 31;   // warp-uniform: the last row of this warp
+    for (int j = 0; j <= jmax; ++j) {
+        const double a = It[(size_t)j * kSolveBlk + i];   // exact zero for j > i
+        const double2* pj = reinterpret_cast<const double2*>(mw_p + j * kWTile);
+#pragma unroll
+        for (int c2 = 0; c2 < kWTile / 2; ++c2) {
+            const double2 v = pj[c2];
+            acc[2 * c2] = fma(a, v.x, acc[2 * c2]);
+            acc[2 * c2 + 1] = fma(a, v.y, acc[2 * c2 + 1]);
+        }
+    }
+    if (i >= w) return;
+    double* wrow = Wc + ((size_t)ib * n + k0 + i) * pw + (ct0 - c_lo);
+#pragma unroll
+    for (int c = 0; c < kWTile; ++c) wrow[c] = acc[c];
+#pragma unroll
+    for (int c = 0; c < kWTile; ++c) {
+        const int cc = ct0 + c;
+        WTc[((size_t)ib * n + cc) * pwt + (k0 + i - (cc / kSolveBlk + 1) * kSolveBlk)] = acc[c];
+    }
+}
+
+static inline double* align_doubles(double* p, size_t bytes) {
+    return (double*)(((uintptr_t)p + bytes - 1) / bytes * bytes);
+}
+// chain-solver arrays inside the Linv area
+static void chain_arrays(const ChainLayout& cl, int B, int n, double* Linv, double** Wc, double** WTc) {
+    double* p = align_doubles(Linv + 2 * (size_t)B * cl.nblk * kSolveBlk * kSolveBlk, 256);
+    *Wc = p;
+    *WTc = p + (size_t)B * n * cl.pw;
+}
+static int g_chain = -1;
+static bool chain_enabled() {
+    if (g_chain < 0) {
+        const char* e = getenv("PDEOP_CHAIN");   // 0: per-block-row launches (A/B testing)
+        g_chain = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return g_chain != 0;
+}
+
 void be_cholesky(stream_t st, int B, int n, int bw, double* Kd, double* Linv, FgmresState* state) {
     cudaStream_t s = (cudaStream_t)st;
     const size_t strideA = (size_t)n * n;
@@ -1239,6 +1312,22 @@ void be_cholesky(stream_t st, int B, int n, int bw, double* Kd, double* Linv, Fg
     const int nblk = (n + kSolveBlk - 1) / kSolveBlk;
     k_trtri<<<dim3(nblk, B), kSolveBlk, 0, s>>>(n, Kd, strideA, Linv, nblk);
     PDEOP_COUNT(1);
+    const ChainLayout cl = be_chain_layout(n, bw);
+    if (cl.use && chain_enabled()) {
+        double *Wc, *WTc;
+        chain_arrays(cl, B, n, Linv, &Wc, &WTc);
+        note(cudaMemsetAsync(WTc, 0, (size_t)B * n * cl.pwt * sizeof(double), s));   // entries W does not store
+        static bool attr_set = false;
+        const int smem = kSolveBlk * kWTile * (int)sizeof(double);
+        if (!attr_set) {
+            note(cudaFuncSetAttribute(k_make_w, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr_set = true;
+        }
+        const double* LinvT = Linv + (size_t)B * nblk * kSolveBlk * kSolveBlk;
+        k_make_w<<<dim3(cdiv(cl.pw, kWTile), nblk - 1, B), kSolveBlk, smem, s>>>(n, nblk, cl.pw, cl.pwt, Kd, strideA, LinvT,
+                                                                                Wc, WTc);
+        PDEOP_COUNT(1);
+    }
     PDEOP_LAUNCH_CHECK();
 }
 
@@ -1368,6 +1457,368 @@ __global__ void __launch_bounds__(kThreads) k_from_band(LevelDev L, const double
     from_band_elem(L, bandv + o, wave + o, w);
 }
 
+// =================================================================================================
+// Chain solver, solve half: y = Wt^-1 u (dir 0, rows of Wc) or v = Wt^-T y (dir 1, rows of WTc) as ONE persistent
+// kernel per direction.  A cluster of 4 CTAs owns one instance; CTA q owns rows 32q..32q+31 of every 128-row block.
+// Per chain step (one block, ascending for dir 0, descending for dir 1) a CTA streams its 32 band rows
+// (~0.45 MB) from HBM with TMA bulk copies issued by two producer threads:
+//   * the "old" part of each row (everything except the block solved in the previous step) goes, in chunks,
+//     through shared-memory stages (mbarrier full/empty pairs, three private stages per consumer warp) and is
+//     consumed by 8 warps, one row each, while the previous block's result is still in flight between the CTAs;
+//   * the "new" part (32 rows x 128 columns of the previous step's block) is prefetched into its own buffer during
+//     the old phase, so that when the previous block arrives only a 32 x 128 product remains on the critical path.
+// Results are exchanged through distributed shared memory: every warp stores its 4 values into all four CTAs'
+// vector windows (a ring of nw blocks) and arrives on their "block ready" mbarriers (release/acquire at cluster
+// scope); no cluster-wide barrier and no kernel boundary sits between two steps.
+// HBM-bound: 8*(band entries) bytes per direction and instance, each read once.
+// =================================================================================================
+constexpr int kChainCta = 4;         // cluster size
+constexpr int kChainRows = kSolveBlk / kChainCta;   // rows of a block per CTA (32)
+static_assert(kChainRows == 32, "the new-block producer maps one lane to one row");
+constexpr int kChainWarps = 8;       // consumer warps
+constexpr int kChainDepth = 3;       // stages per consumer warp (each warp owns its stages: a parity wait is only
+                                     // meaningful for a waiter that observes every phase of its barrier in order)
+constexpr int kChainStages = kChainWarps * kChainDepth;
+constexpr int kChainCH = 848;        // doubles per stage (one chunk of a row's old part): 24 stages = 159 KB in flight
+constexpr int kChainThreads = (kChainWarps + 2) * 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t a, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t a, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t a) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+// bounded spin: a protocol error traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
+    for (long long spin = 0;; ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (spin > (1LL << 22)) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t a, uint32_t parity) {
+    for (long long spin = 0;; ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (spin > (1LL << 22)) __trap();
+    }
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t a, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(a),
+        "r"(rank)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+
+struct ChainRow {
+    const double* new_src;   // previous step's block columns of this row (null: none)
+    int new_len;
+    const double* old_src;   // everything older
+    int old_len;             // multiple of 32
+};
+
+// geometry of local row j of step block k; v0 = vector index of old_src[0]
+__device__ __forceinline__ ChainRow chain_row(int dir, int n, int nblk, int pw, int pwt, const double* Wi, int k, int s,
+                                              int g) {
+    ChainRow r;
+    r.new_src = nullptr;
+    r.new_len = 0;
+    r.old_src = nullptr;
+    r.old_len = 0;
+    if (g >= n || s == 0) return r;
+    const int k0 = k * kSolveBlk;
+    if (dir == 0) {
+        const int c_lo = k0 - pw > 0 ? k0 - pw : 0;
+        const int ncols = k0 - c_lo;
+        const double* base = Wi + (size_t)g * pw;
+        r.new_src = base + (ncols - kSolveBlk);
+        r.new_len = kSolveBlk;
+        r.old_src = base;
+        r.old_len = ncols - kSolveBlk;
+    } else {
+        const double* base = Wi + (size_t)g * pwt;
+        const int left = n - (k + 1) * kSolveBlk;
+        r.new_src = base;
+        r.new_len = left < kSolveBlk ? left : kSolveBlk;
+        int rho = (g + pw) / kSolveBlk;   // last block row whose band reaches column g
+        if (rho > nblk - 1) rho = nblk - 1;
+        r.old_src = base + kSolveBlk;
+        r.old_len = rho > k + 1 ? (rho - (k + 1)) * kSolveBlk : 0;
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(kChainThreads, 1) k_band_chain(int dir, int n, int nblk, int pw, int pwt, int nw,
+                                                                const double* __restrict__ W,
+                                                                const double* __restrict__ vin,
+                                                                double* __restrict__ vout, const int* done) {
+    if (done && *done) return;
+    extern __shared__ __align__(128) unsigned char ch_smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int q = (int)cluster.block_rank();
+    const int ib = blockIdx.x / kChainCta;
+    double* newbuf = reinterpret_cast<double*>(ch_smem);                  // [kChainRows][kSolveBlk]
+    constexpr int ns = kChainStages;
+    double* ring = newbuf + kChainRows * kSolveBlk;                       // [kChainStages][kChainCH]
+    double* win = ring + (size_t)ns * kChainCH;                           // [nw][kSolveBlk]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(win + (size_t)nw * kSolveBlk);
+    // bars: full[ns] | empty[ns] | full_new | empty_new | ready[2]
+    const uint32_t b_full = smem_u32(bars), b_empty = smem_u32(bars + ns);
+    const uint32_t b_full_new = smem_u32(bars + 2 * ns), b_empty_new = smem_u32(bars + 2 * ns + 1);
+    const uint32_t b_ready = smem_u32(bars + 2 * ns + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < kChainRows * kSolveBlk; i += blockDim.x) newbuf[i] = 0.0;
+    for (int i = tid; i < nw * kSolveBlk; i += blockDim.x) win[i] = 0.0;
+    if (tid == 0) {
+        for (int i = 0; i < ns; ++i) {
+            mbar_init(b_full + 8 * i, 1);
+            mbar_init(b_empty + 8 * i, 1);
+        }
+        mbar_init(b_full_new, 1);
+        mbar_init(b_empty_new, kChainWarps);
+        mbar_init(b_ready, kChainWarps * kChainCta);
+        mbar_init(b_ready + 8, kChainWarps * kChainCta);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    cluster.sync();   // barriers and windows of all four CTAs are ready before anyone stores into them
+
+    const size_t pitch = dir == 0 ? (size_t)pw : (size_t)pwt;
+    const double* Wi = W + (size_t)ib * n * pitch;
+    const double* vi = vin + (size_t)ib * n;
+    double* vo = vout + (size_t)ib * n;
+
+    if (warp == kChainWarps) {
+        // ---- producers of the old chunks: lane wv feeds consumer warp wv (a single issuing thread is too slow:
+        // ~0.25 us per chunk of address arithmetic, waiting and issuing, 64 chunks per step).  Consumer warp wv owns
+        // rows wv + 8m and stages wv*depth ..; its chunks are numbered lq in its own order (row, then chunk),
+        // stage = lq % depth, parity = (lq / depth) & 1.
+        if (lane < kChainWarps) {
+            const int wv = lane;
+            unsigned lq = 0;
+            for (int s = 1; s < nblk; ++s) {
+                const int k = dir == 0 ? s : nblk - 1 - s;
+                const int gl = k * kSolveBlk + q * kChainRows;
+                const ChainRow last = chain_row(dir, n, nblk, pw, pwt, Wi, k, s, min(gl + kChainRows - 1, n - 1));
+                const int nch = (last.old_len + kChainCH - 1) / kChainCH;
+                for (int m = 0; m < kChainRows / kChainWarps; ++m) {
+                    const ChainRow r = chain_row(dir, n, nblk, pw, pwt, Wi, k, s, gl + wv + kChainWarps * m);
+                    for (int c = 0; c < nch; ++c, ++lq) {
+                        const unsigned stage = (unsigned)wv * kChainDepth + lq % kChainDepth;
+                        const unsigned par = (lq / kChainDepth) & 1u;
+                        mbar_wait(b_empty + 8 * stage, par ^ 1u);
+                        int len = r.old_len - c * kChainCH;
+                        if (len > kChainCH) len = kChainCH;
+                        if (len > 0) {
+                            mbar_expect_tx(b_full + 8 * stage, (uint32_t)len * 8u);
+                            bulk_g2s(smem_u32(ring + (size_t)stage * kChainCH), r.old_src + (size_t)c * kChainCH,
+                                     (uint32_t)len * 8u, b_full + 8 * stage);
+                        } else {
+                            mbar_arrive(b_full + 8 * stage);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == kChainWarps + 1) {
+        // ---- producers of the new-block buffer: lane j copies local row j (kChainRows == 32) ----
+        for (int s = 1; s < nblk; ++s) {
+            const int k = dir == 0 ? s : nblk - 1 - s;
+            const int gl = k * kSolveBlk + q * kChainRows;
+            const ChainRow r = chain_row(dir, n, nblk, pw, pwt, Wi, k, s, gl + lane);
+            uint32_t total = (uint32_t)r.new_len * 8u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+            if (lane == 0) {
+                mbar_wait(b_empty_new, ((unsigned)(s - 1) & 1u) ^ 1u);
+                mbar_expect_tx(b_full_new, total);
+            }
+            __syncwarp();
+            if (r.new_len > 0)
+                bulk_g2s(smem_u32(newbuf + lane * kSolveBlk), r.new_src, (uint32_t)r.new_len * 8u, b_full_new);
+        }
+    } else {
+        // ---- consumers: warp wv owns local rows wv, wv+8, ... ----
+        const int wv = warp;
+        constexpr int RW = kChainRows / kChainWarps;   // rows per warp (4)
+        unsigned seq_base = 0;
+        for (int s = 0; s < nblk; ++s) {
+            const int k = dir == 0 ? s : nblk - 1 - s;
+            const int kn = dir == 0 ? k - 1 : k + 1;
+            const int gl = k * kSolveBlk + q * kChainRows;
+            double uin[RW], acc[RW];
+#pragma unroll
+            for (int m = 0; m < RW; ++m) {
+                const int g = gl + wv + kChainWarps * m;
+                uin[m] = g < n ? vi[g] : 0.0;
+                acc[m] = 0.0;
+            }
+            int nch = 0;
+            if (s > 0) {
+                const ChainRow last = chain_row(dir, n, nblk, pw, pwt, Wi, k, s, min(gl + kChainRows - 1, n - 1));
+                nch = (last.old_len + kChainCH - 1) / kChainCH;
+                const int k0 = k * kSolveBlk;
+                const int v0 = dir == 0 ? (k0 - pw > 0 ? k0 - pw : 0) : (k + 2) * kSolveBlk;
+                // old phase: needs blocks solved two or more steps ago, all delivered before the previous new phase
+#pragma unroll
+                for (int m = 0; m < RW; ++m) {
+                    const int j = wv + kChainWarps * m;
+                    const ChainRow r = chain_row(dir, n, nblk, pw, pwt, Wi, k, s, gl + j);
+                    for (int c = 0; c < nch; ++c) {
+                        const unsigned lq = seq_base + (unsigned)(m * nch + c);
+                        const unsigned stage = (unsigned)wv * kChainDepth + lq % kChainDepth;
+                        const unsigned par = (lq / kChainDepth) & 1u;
+                        mbar_wait(b_full + 8 * stage, par);
+                        int len = r.old_len - c * kChainCH;
+                        if (len > kChainCH) len = kChainCH;
+                        if (len > 0) {
+                            const double* wc = ring + (size_t)stage * kChainCH;
+                            const int gv = v0 + c * kChainCH + 2 * lane;   // vector index of this lane's first pair
+                            int slot = (gv / kSolveBlk) % nw, off = gv % kSolveBlk;
+                            double a = acc[m];
+                            for (int e = 2 * lane; e < len; e += 64) {
+                                const double2 wv2 = *reinterpret_cast<const double2*>(wc + e);
+                                const double2 yv2 = *reinterpret_cast<const double2*>(win + slot * kSolveBlk + off);
+                                a = fma(wv2.x, yv2.x, a);
+                                a = fma(wv2.y, yv2.y, a);
+                                off += 64;
+                                if (off >= kSolveBlk) {
+                                    off -= kSolveBlk;
+                                    slot = slot + 1 == nw ? 0 : slot + 1;
+                                }
+                            }
+                            acc[m] = a;
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(b_empty + 8 * stage);
+                    }
+                }
+                seq_base += (unsigned)(RW * nch);
+                // new phase: the previous step's block has arrived in this CTA's window
+                mbar_wait_cluster(b_ready + 8 * ((unsigned)(s - 1) & 1u), ((unsigned)(s - 1) >> 1) & 1u);
+                mbar_wait(b_full_new, (unsigned)(s - 1) & 1u);
+                const double* yn = win + (kn % nw) * kSolveBlk;
+#pragma unroll
+                for (int m = 0; m < RW; ++m) {
+                    const double* wr = newbuf + (wv + kChainWarps * m) * kSolveBlk;
+                    double a = acc[m];
+#pragma unroll
+                    for (int it = 0; it < kSolveBlk / 64; ++it) {
+                        const double2 wv2 = *reinterpret_cast<const double2*>(wr + 64 * it + 2 * lane);
+                        const double2 yv2 = *reinterpret_cast<const double2*>(yn + 64 * it + 2 * lane);
+                        a = fma(wv2.x, yv2.x, a);
+                        a = fma(wv2.y, yv2.y, a);
+                    }
+                    acc[m] = a;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(b_empty_new);
+            }
+            // reduce, finish, and deliver this warp's 8 values to all four CTAs
+            double mine = 0.0;
+#pragma unroll
+            for (int m = 0; m < RW; ++m) {
+                const double tot = warp_sum(acc[m]);
+                const double yv = uin[m] - tot;
+                if ((lane & (RW - 1)) == m) mine = yv;
+            }
+            {
+                const int m = lane & (RW - 1), dst = lane / RW;   // lanes 0..RW*4-1 = 4 CTAs x RW rows
+                const int jl = wv + kChainWarps * m;
+                const int g = gl + jl;
+                if (dst < kChainCta && g < n) {
+                    double* slotp = win + (k % nw) * kSolveBlk + q * kChainRows + jl;
+                    *cluster.map_shared_rank(slotp, dst) = mine;
+                    if (dst == 0) vo[g] = mine;
+                }
+            }
+            __syncwarp();
+            if (lane < kChainCta) mbar_arrive_remote(b_ready + 8 * ((unsigned)s & 1u), (uint32_t)lane);
+        }
+    }
+    __syncthreads();
+    cluster.sync();   // no CTA leaves while others may still store into its window or arrive on its barriers
+}
+
+static size_t chain_smem_bytes(int nw) {
+    return ((size_t)kChainRows * kSolveBlk + (size_t)kChainStages * kChainCH + (size_t)nw * kSolveBlk) * sizeof(double) +
+           (size_t)(2 * kChainStages + 4) * 8;
+}
+
+// y_k = M_kk t_k for every block at once (grid z = block): the block-diagonal products that frame the chain
+__global__ void __launch_bounds__(256) k_blk_mv_all(int n, const double* __restrict__ Linv, int nblk, const double* t,
+                                                    double* y, int upper, const int* done) {
+    if (done && *done) return;
+    __shared__ double ts[kSolveBlk];
+    const int ib = blockIdx.y, kb = blockIdx.z;
+    const int k0 = kb * kSolveBlk;
+    const int w = k0 + kSolveBlk < n ? kSolveBlk : n - k0;
+    for (int i = threadIdx.x; i < w; i += blockDim.x) ts[i] = t[(size_t)ib * n + k0 + i];
+    __syncthreads();
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= w) return;
+    const int lane = threadIdx.x & 31;
+    const double* Ir = Linv + ((size_t)ib * nblk + kb) * kSolveBlk * kSolveBlk + (size_t)row * kSolveBlk;
+    double a = 0.0;
+    const int c0 = upper ? (row & ~31) : 0, c1 = upper ? w : row + 1;
+    for (int c = c0 + lane; c < c1; c += 32)
+        if (!upper || c >= row) a += Ir[c] * ts[c];
+    a = warp_sum(a);
+    if (lane == 0) y[(size_t)ib * n + k0 + row] = a;
+}
+
+static void launch_chain(cudaStream_t s, int dir, int B, int n, const ChainLayout& cl, const double* W, const double* vin,
+                         double* vout, const int* done) {
+    const int nw = cl.nbmax + 1;
+    const size_t smem = chain_smem_bytes(nw);
+    static size_t set_for = 0;
+    if (smem > set_for) {
+        note(cudaFuncSetAttribute(k_band_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        set_for = smem;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(B * kChainCta));
+    cfg.blockDim = dim3(kChainThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kChainCta;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    note(cudaLaunchKernelEx(&cfg, k_band_chain, dir, n, cl.nblk, cl.pw, cl.pwt, nw, W, vin, vout, done));
+    PDEOP_COUNT(1);
+}
+
 void be_chol_solve(stream_t st, const LevelDev& L, int B, const double* Lf, const double* Linv, const double* rhs,
                    double* out, double* work, const int* done) {
     cudaStream_t s = (cudaStream_t)st;
@@ -1380,6 +1831,24 @@ void be_chol_solve(stream_t st, const LevelDev& L, int B, const double* Lf, cons
     double* y = work + (size_t)B * n;   // solution in band ordering
     k_to_band<<<dim3(cdiv(L.G, kThreads), B), kThreads, 0, s>>>(L, rhs, rb, done);
     PDEOP_COUNT(1);
+    const ChainLayout cl = be_chain_layout(n, bw);
+    if (cl.use && chain_enabled()) {
+        // L^-1 = Wt^-1 D^-1, L^-T = D^-T Wt^-T: block-diagonal product, two chains, block-diagonal product
+        double *Wc, *WTc;
+        chain_arrays(cl, B, n, const_cast<double*>(Linv), &Wc, &WTc);
+        k_blk_mv_all<<<dim3(kSolveBlk / 8, B, nblk), 256, 0, s>>>(n, Linv, nblk, rb, y, 0, done);
+        launch_chain(s, 0, B, n, cl, Wc, y, rb, done);
+        if (getenv("PDEOP_CHAIN_DEBUG")) {   // debugging aid: return L^-1 rhs
+            k_from_band<<<dim3(cdiv(L.G, kThreads), B), kThreads, 0, s>>>(L, rb, out, done);
+            return;
+        }
+        launch_chain(s, 1, B, n, cl, WTc, rb, y, done);
+        k_blk_mv_all<<<dim3(kSolveBlk / 8, B, nblk), 256, 0, s>>>(n, LinvT, nblk, y, rb, 1, done);
+        k_from_band<<<dim3(cdiv(L.G, kThreads), B), kThreads, 0, s>>>(L, rb, out, done);
+        PDEOP_COUNT(3);
+        PDEOP_LAUNCH_CHECK();
+        return;
+    }
     // forward: y = L^-1 rb.  Per block row: t = rb_k - L[k, band] y (GEMV, in place in rb), y_k = Linv_kk t
     for (int kb = 0; kb < nblk; ++kb) {
         const int k0 = kb * kSolveBlk;
@@ -1393,6 +1862,10 @@ void be_chol_solve(stream_t st, const LevelDev& L, int B, const double* Lf, cons
         }
         k_blk_mv<<<dim3(cdiv(w, 8), B), 256, 0, s>>>(n, Linv, nblk, kb, w, rb, y, 0, done);
         PDEOP_COUNT(1);
+    }
+    if (getenv("PDEOP_CHAIN_DEBUG")) {   // debugging aid: return L^-1 rhs
+        k_from_band<<<dim3(cdiv(L.G, kThreads), B), kThreads, 0, s>>>(L, y, out, done);
+        return;
     }
     // backward: y <- L^-T y.  Per block row (descending): z_k = Linv_kk^T y_k (into rb), then the update kernel
     // stores z_k into y and subtracts L[k rows, c]^T z_k from the band columns left of the block

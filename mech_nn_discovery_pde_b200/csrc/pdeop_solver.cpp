@@ -239,7 +239,7 @@ extern "C" int pdeop_plan_create(int d, const int* dims, int order, int batch, i
     pl->off_Kd = poff;
     poff += (size_t)batch * pl->nc * pl->nc;
     pl->off_Linv = poff;
-    poff += 2 * (size_t)batch * ((pl->nc + kSolveBlk - 1) / kSolveBlk) * kSolveBlk * kSolveBlk;  // inverse + transpose
+    poff += be_chol_linv_doubles(batch, pl->nc, Lc.bw);   // inverse diagonal blocks (+ transposes, + scaled band)
     pl->persist_doubles = poff;
     *out = pl;
     return 0;

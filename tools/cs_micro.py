@@ -21,6 +21,7 @@ e1.record(); torch.cuda.synchronize()
 print("setup+factor (incl. host work) ms", e0.elapsed_time(e1))
 lc = n_grid - 1
 nc = sr.level_n(lc)
+torch.manual_seed(7)
 b = torch.randn(B * nc, dtype=torch.float64, device=dev); out = torch.zeros_like(b)
 cfg = sr.plan.cfg(False)
 def call():
@@ -31,3 +32,8 @@ e0.record()
 for _ in range(reps): call()
 e1.record(); torch.cuda.synchronize()
 print(f"coarse solve n={nc} B={B}: {e0.elapsed_time(e1)/reps:.3f} ms per solve (incl. pack/unpack)")
+tag = os.environ.get("TAG")
+if tag:
+    os.makedirs("gpurun_out", exist_ok=True)
+    np.save(f"gpurun_out/cs_out_{tag}.npy", out.cpu().numpy())
+    print("checksum", float(out.abs().sum()), "finite", bool(torch.isfinite(out).all()))
