@@ -1467,9 +1467,9 @@ __global__ void __launch_bounds__(kThreads) k_from_band(LevelDev L, const double
 //     consumed by 8 warps, one row each, while the previous block's result is still in flight between the CTAs;
 //   * the "new" part (32 rows x 128 columns of the previous step's block) is prefetched into its own buffer during
 //     the old phase, so that when the previous block arrives only a 32 x 128 product remains on the critical path.
-// Results are exchanged through distributed shared memory: every warp stores its 4 values into all four CTAs'
-// vector windows (a ring of nw blocks) and arrives on their "block ready" mbarriers (release/acquire at cluster
-// scope); no cluster-wide barrier and no kernel boundary sits between two steps.
+// Results are exchanged through distributed shared memory: every warp sends its 4 values into all four CTAs'
+// vector windows (a ring of nw blocks) with st.async, which completes transaction bytes on the receiving CTA's
+// "block ready" mbarrier; no fence, no cluster-wide barrier and no kernel boundary sits between two steps.
 // HBM-bound: 8*(band entries) bytes per direction and instance, each read once.
 // =================================================================================================
 constexpr int kChainCta = 4;         // cluster size
@@ -1528,6 +1528,17 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t a, uint32_t rank) {
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
         "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(a),
         "r"(rank)
+        : "memory");
+}
+// asynchronous 8-byte store into CTA `rank`'s shared memory (same offset as the local address) that completes
+// 8 transaction bytes on that CTA's mbarrier: data and "it has arrived" travel together, no release fence
+__device__ __forceinline__ void st_async_remote(uint32_t local_addr, double v, uint32_t local_mbar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra, rm;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %3;\n\t"
+        "mapa.shared::cluster.u32 rm, %2, %3;\n\t"
+        "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [ra], %1, [rm];\n\t}" ::"r"(local_addr),
+        "l"(__double_as_longlong(v)), "r"(local_mbar), "r"(rank)
         : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
@@ -1602,8 +1613,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_band_chain(int dir, int n,
         }
         mbar_init(b_full_new, 1);
         mbar_init(b_empty_new, kChainWarps);
-        mbar_init(b_ready, kChainWarps * kChainCta);
-        mbar_init(b_ready + 8, kChainWarps * kChainCta);
+        mbar_init(b_ready, 1);       // one local arming arrival per phase + 8 bytes per delivered value
+        mbar_init(b_ready + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -1668,10 +1679,23 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_band_chain(int dir, int n,
         const int wv = warp;
         constexpr int RW = kChainRows / kChainWarps;   // rows per warp (4)
         unsigned seq_base = 0;
+#ifdef PDEOP_GS_TIMING
+        long long tOld = 0, tReady = 0, tNew = 0, tFin = 0;
+#endif
         for (int s = 0; s < nblk; ++s) {
+#ifdef PDEOP_GS_TIMING
+            const long long c0 = clock64();
+            long long c1 = c0, c2 = c0, c3 = c0;
+#endif
             const int k = dir == 0 ? s : nblk - 1 - s;
             const int kn = dir == 0 ? k - 1 : k + 1;
             const int gl = k * kSolveBlk + q * kChainRows;
+            if (wv == 0 && lane == 0) {
+                // arm this step's "block ready" phase: its previous phase (step s-2) completed before this warp's
+                // previous new phase; deliveries that arrive before the arming just run the byte count negative
+                const int wk = n - k * kSolveBlk < kSolveBlk ? n - k * kSolveBlk : kSolveBlk;
+                mbar_expect_tx(b_ready + 8 * ((unsigned)s & 1u), (uint32_t)wk * 8u);
+            }
             double uin[RW], acc[RW];
 #pragma unroll
             for (int m = 0; m < RW; ++m) {
@@ -1720,9 +1744,18 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_band_chain(int dir, int n,
                     }
                 }
                 seq_base += (unsigned)(RW * nch);
+#ifdef PDEOP_GS_TIMING
+                c1 = clock64();
+#endif
                 // new phase: the previous step's block has arrived in this CTA's window
                 mbar_wait_cluster(b_ready + 8 * ((unsigned)(s - 1) & 1u), ((unsigned)(s - 1) >> 1) & 1u);
+#ifdef PDEOP_GS_TIMING
+                c2 = clock64();
+#endif
                 mbar_wait(b_full_new, (unsigned)(s - 1) & 1u);
+#ifdef PDEOP_GS_TIMING
+                c3 = clock64();
+#endif
                 const double* yn = win + (kn % nw) * kSolveBlk;
 #pragma unroll
                 for (int m = 0; m < RW; ++m) {
@@ -1753,14 +1786,28 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_band_chain(int dir, int n,
                 const int jl = wv + kChainWarps * m;
                 const int g = gl + jl;
                 if (dst < kChainCta && g < n) {
-                    double* slotp = win + (k % nw) * kSolveBlk + q * kChainRows + jl;
-                    *cluster.map_shared_rank(slotp, dst) = mine;
+                    const double* slotp = win + (k % nw) * kSolveBlk + q * kChainRows + jl;
+                    st_async_remote(smem_u32(slotp), mine, b_ready + 8 * ((unsigned)s & 1u), (uint32_t)dst);
                     if (dst == 0) vo[g] = mine;
                 }
             }
-            __syncwarp();
-            if (lane < kChainCta) mbar_arrive_remote(b_ready + 8 * ((unsigned)s & 1u), (uint32_t)lane);
+#ifdef PDEOP_GS_TIMING
+            const long long c4 = clock64();
+            tOld += c1 - c0;
+            tReady += c2 - c1;
+            tNew += c3 - c2;
+            tFin += c4 - c3;
+#endif
         }
+#ifdef PDEOP_GS_TIMING
+        if (blockIdx.x == 0 && tid == 0) {
+            g_gs_dbg[0] += nblk;
+            g_gs_dbg[1] += tOld;
+            g_gs_dbg[2] += tReady;
+            g_gs_dbg[3] += tNew;
+            g_gs_dbg[4] += tFin;
+        }
+#endif
     }
     __syncthreads();
     cluster.sync();   // no CTA leaves while others may still store into its window or arrive on its barriers
