@@ -20,6 +20,12 @@
 
 namespace cg = cooperative_groups;
 
+// load policy of the Gauss-Seidel iterate.  An L2 evict-last hint on these loads (createpolicy + ld.L2::cache_hint)
+// was measured and changes nothing once the streamed operands carry evict-first (ld_stream).
+#ifndef PDEOP_GS_LD
+#define PDEOP_GS_LD LdPlain
+#endif
+
 namespace pdeop {
 
 static thread_local cudaError_t g_cuda_err = cudaSuccess;
@@ -245,28 +251,36 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gs_cluster(LevelDev L, const 
         hs = hss;
     }
     const int steps = L.S + kGsLag * (nsweeps - 1);
-    for (int t = 0; t < steps; ++t) {
-        // active hyperplanes of this step: s_k = t - lag*k for sweep k
-        int k_lo = (t - (L.S - 1) + kGsLag - 1) / kGsLag;
+    // points of step t: the hyperplanes s_k = t - lag*k of the sweeps k in flight, concatenated
+    auto step_sweeps = [&](int t, int& k_lo, int& k_hi) -> int {
+        k_lo = (t - (L.S - 1) + kGsLag - 1) / kGsLag;
         if (k_lo < 0) k_lo = 0;
-        int k_hi = t / kGsLag;
+        k_hi = t / kGsLag;
         if (k_hi > nsweeps - 1) k_hi = nsweeps - 1;
         int total = 0;
         for (int k = k_lo; k <= k_hi; ++k) {
             const int s = t - kGsLag * k;
             total += hs[s + 1] - hs[s];
         }
+        return total;
+    };
+    auto point_of = [&](int t, int k_lo, int k_hi, int idx) -> int {
+        int rem = idx;
+        for (int k = k_lo; k <= k_hi; ++k) {
+            const int s = t - kGsLag * k;
+            const int h0 = hs[s], cnt = hs[s + 1] - h0;
+            if (rem < cnt) return h0 + rem;
+            rem -= cnt;
+        }
+        return -1;
+    };
+    // (Prefetching the next point's coordinates, as the pipelined kernel does, was measured here and is slower:
+    // 2.90 vs 2.83 ms per fine-level call.)
+    for (int t = 0; t < steps; ++t) {
+        int k_lo, k_hi;
+        const int total = step_sweeps(t, k_lo, k_hi);
         for (int idx = tid; idx < total; idx += nthreads) {
-            int rem = idx, w = -1;
-            for (int k = k_lo; k <= k_hi; ++k) {
-                const int s = t - kGsLag * k;
-                const int h0 = hs[s], cnt = hs[s + 1] - h0;
-                if (rem < cnt) {
-                    w = h0 + rem;
-                    break;
-                }
-                rem -= cnt;
-            }
+            const int w = point_of(t, k_lo, k_hi, idx);
             gs_elem<D, LD, PITCH>(L, rbuse, Tuse, coef + o, dinv + o, b + o, x + o, w);
         }
         // release/acquire at cluster scope; the acquire side invalidates L1 (CCTL.IVALL), so the next
@@ -285,7 +299,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gs_cluster(LevelDev L, const 
 // cluster barrier:
 //     A(t): finish the points of step t   = stashed partial residual - backward-1 couplings, channel solve, store
 //     barrier.cluster.arrive.release
-//     B(t): pre-gather for the points of step t+1 (gs_pre_elem) into the stash; L2 prefetch of what A(t+1) reads
+//     B(t): pre-gather for the points of step t+1 (gs_pre_elem) into the stash
 //     barrier.cluster.wait.acquire
 // The critical path between two barriers is one batch of loads plus the channel solve; the long gather runs in
 // the shadow of the barrier and of the other CTAs' A halves.  The stash of a thread's first point of a step stays
@@ -298,6 +312,7 @@ __device__ __forceinline__ void cluster_arrive_release() {
 __device__ __forceinline__ void cluster_wait_acquire() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 constexpr int kStashSlots = 8;   // doubles per stashed point: M <= 7 residuals + (wave index, coord) packed
@@ -413,14 +428,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_gs_pipe(LevelDev L, const double
             const int cf_next = w_next >= 0 ? L.coord[w_next] : 0;
             int i0, i1, i2;
             unpack_coord(cf, i0, i1, i2);
-            // what the finishing half reads from DRAM-cold streams: pull it into L2 now
+            // what the finishing half reads from DRAM-cold streams: pull it into L2 now.  (Helps on the levels
+            // this kernel is used for by default; on the fine level, where the L2 thrashes, it is a loss: the
+            // prefetch allocates with normal priority and undoes the evict-first hint of ld_stream.)
 #pragma unroll
             for (int m = 0; m < M; ++m) {
                 prefetch_l2(dvo + ((unsigned)m * (unsigned)G + (unsigned)w));
                 if (coord_eq(cf)) prefetch_l2(co + ((unsigned)m * (unsigned)G + (unsigned)w));
             }
             double r[M];
-            gs_pre_elem<D, LdPlain, PITCH>(L, rbuse, Tuse, bo, xo, w, i0, i1, i2, r);
+            gs_pre_elem<D, PDEOP_GS_LD, PITCH>(L, rbuse, Tuse, bo, xo, w, i0, i1, i2, r);
             if (n == 0) {   // a thread's first point of a step: shared-memory stash (private slot, no sync needed)
 #pragma unroll
                 for (int m = 0; m < M; ++m) st0[m * THREADS] = r[m];
@@ -458,7 +475,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gs_pipe(LevelDev L, const double
             const int w = __double2loint(pk), cf = __double2hiint(pk);
             int i0, i1, i2;
             unpack_coord(cf, i0, i1, i2);
-            gs_fin_elem<D, LdPlain, PITCH>(L, rbuse, Tuse, co, dvo, xo, w, i0, i1, i2, coord_eq(cf), r);
+            gs_fin_elem<D, PDEOP_GS_LD, PITCH>(L, rbuse, Tuse, co, dvo, xo, w, i0, i1, i2, coord_eq(cf), r);
         }
         for (int n = 1; n < nA; ++n) {
             const double* sp = st + (size_t)(n - 1) * kStashSlots * nthreads;
@@ -469,7 +486,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gs_pipe(LevelDev L, const double
             const int w = __double2loint(pk), cf = __double2hiint(pk);
             int i0, i1, i2;
             unpack_coord(cf, i0, i1, i2);
-            gs_fin_elem<D, LdPlain, PITCH>(L, rbuse, Tuse, co, dvo, xo, w, i0, i1, i2, coord_eq(cf), r);
+            gs_fin_elem<D, PDEOP_GS_LD, PITCH>(L, rbuse, Tuse, co, dvo, xo, w, i0, i1, i2, coord_eq(cf), r);
         }
         // release the stores of A(t); the acquire side invalidates L1 (CCTL.IVALL), so the plain loads of the
         // next halves see what the other CTAs of the cluster wrote
@@ -577,7 +594,7 @@ static void fit_cluster_wave(cudaLaunchConfig_t& cfg, K kern, int B) {
 template <int D, int THREADS, int MINB, int PS, bool SINGLE>
 static void launch_gs_inst(cudaLaunchConfig_t& cfg, const LevelDev& L, const double* T, const double* coef,
                            const double* dinv, const double* b, double* x, int nsweeps, const int* done) {
-    auto kern = k_gs_cluster<D, THREADS, MINB, LdPlain, PS, SINGLE>;
+    auto kern = k_gs_cluster<D, THREADS, MINB, PDEOP_GS_LD, PS, SINGLE>;
     size_t smem = 0;
     if (PS > 0) {
         smem = (size_t)D * kTabEntries * PS * sizeof(double) + ((size_t)(L.S + 8) * L.N[0] + 8 + L.S + 1) * sizeof(int);

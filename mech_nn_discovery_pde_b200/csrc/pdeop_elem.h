@@ -29,6 +29,17 @@ struct LdL2 {
     }
 };
 
+// Streaming load (ld.global.cs: evict-first in L1 and L2) for data a sweep touches once per point (right-hand
+// side, equation coefficients, reciprocal diagonals): keeps the L2 for the iterate, whose every value is gathered
+// 24 times within +-4 wavefront steps.  PDEOP_NO_STREAM_HINT disables it (A/B testing).
+PDEOP_HD double ld_stream(const double* p) {
+#if defined(__CUDA_ARCH__) && !defined(PDEOP_NO_STREAM_HINT)
+    return __ldcs(p);
+#else
+    return *p;
+#endif
+}
+
 #ifndef PDEOP_ATOMIC_ADD
 #if defined(__CUDA_ARCH__)
 #define PDEOP_ATOMIC_ADD(p, v) atomicAdd((p), (v))
@@ -292,7 +303,7 @@ PDEOP_HD void k_gather(const LevelDev& L, const int* __restrict__ rowbase, const
         if (a + 1 < D) gather_axis_load<D, LD, SPLIT>(L, rb, x, a + 1, idx[3 - D + a + 1], i1, nb[a + 1]);
         if (BSUB && a == D - 1) {
 #pragma unroll
-            for (int m = 0; m < M; ++m) bl[m] = b[(unsigned)m * (unsigned)L.G + w];
+            for (int m = 0; m < M; ++m) bl[m] = ld_stream(b + ((unsigned)m * (unsigned)L.G + w));
         }
         PDEOP_LOAD_FENCE();
         gather_axis_fma<D, PITCH, SPLIT>(L, T, a, idx[3 - D + a], nb[a], acc);
@@ -373,7 +384,7 @@ PDEOP_HD void load_local(const LevelDev& L, const double* __restrict__ T, const 
     const bool eq = flags & 1;
 #pragma unroll
     for (int m = 0; m < 1 + 2 * D; ++m) {
-        pl.c[m] = eq ? coef[m * G + w] : 0.0;
+        pl.c[m] = eq ? coef[m * G + w] : 0.0;   // (ld_stream here makes K apply 25 % slower: measured)
         pl.ini[m] = (double)((flags >> (4 + 2 * m)) & 3);
     }
     load_axis_local<D, kTabPitch>(T, i0, i1, i2, pl);
@@ -454,24 +465,38 @@ PDEOP_HD void gs_pre_elem(const LevelDev& L, const int* __restrict__ rowbase, co
     k_gather<D, LD, PITCH, true, true>(L, rowbase, T, x, b, (unsigned)w, i0, i1, i2, r);
 }
 
-template <int D, class LD, int PITCH>
-PDEOP_HD void gs_fin_elem(const LevelDev& L, const int* __restrict__ rowbase, const double* __restrict__ T,
-                          const double* __restrict__ coef, const double* __restrict__ dinv, double* x, int w, int i0,
-                          int i1, int i2, bool eq, double r[1 + 2 * D]) {
+// operands of the finishing half: old own-point values, equation coefficients, reciprocal diagonals, backward
+// distance-1 neighbours -- one batch of loads
+template <int D>
+struct FinLoads {
+    double xl[1 + 2 * D], c[1 + 2 * D], di[1 + 2 * D];
+    Back1<D> nb;
+};
+
+template <int D, class LD>
+PDEOP_HD void gs_fin_load(const LevelDev& L, const int* __restrict__ rowbase, const double* __restrict__ coef,
+                          const double* __restrict__ dinv, const double* x, int w, int i0, int i1, int i2, bool eq,
+                          FinLoads<D>& f) {
     constexpr int M = 1 + 2 * D;
     const unsigned G = (unsigned)L.G, uw = (unsigned)w;
-    // one batch of loads: old own-point values, equation coefficients, reciprocal diagonals, backward neighbours
-    double xl[M], c[M], di[M];
-    Back1<D> nb;
-    gs_back1_load<D, LD>(L, rowbase, x, i0, i1, i2, nb);
+    gs_back1_load<D, LD>(L, rowbase, x, i0, i1, i2, f.nb);
 #pragma unroll
     for (int m = 0; m < M; ++m) {
-        xl[m] = LD::ld(x + ((unsigned)m * G + uw));
-        c[m] = eq ? coef[(unsigned)m * G + uw] : 0.0;
-        di[m] = dinv[(unsigned)m * G + uw];
+        f.xl[m] = LD::ld(x + ((unsigned)m * G + uw));
+        f.c[m] = eq ? ld_stream(coef + ((unsigned)m * G + uw)) : 0.0;
+        f.di[m] = ld_stream(dinv + ((unsigned)m * G + uw));
     }
-    PDEOP_LOAD_FENCE();
-    gs_back1_apply<D, PITCH>(T, i0, i1, i2, nb, r);
+}
+
+template <int D, int PITCH>
+PDEOP_HD void gs_fin_compute(const LevelDev& L, const double* __restrict__ T, double* x, int w, int i0, int i1, int i2,
+                             FinLoads<D>& f, double r[1 + 2 * D]) {
+    constexpr int M = 1 + 2 * D;
+    const unsigned G = (unsigned)L.G, uw = (unsigned)w;
+    double* xl = f.xl;
+    const double* c = f.c;
+    const double* di = f.di;
+    gs_back1_apply<D, PITCH>(T, i0, i1, i2, f.nb, r);
     PointLocal<D> pl;
     load_axis_local<D, PITCH>(T, i0, i1, i2, pl);
     // Canonical arithmetic (every kernel that inlines this body, and the host emulator, produce the same bits):
@@ -513,17 +538,36 @@ PDEOP_HD void gs_fin_elem(const LevelDev& L, const int* __restrict__ rowbase, co
     for (int m = 0; m < M; ++m) x[(unsigned)m * G + uw] = xl[m];
 }
 
-// both halves back to back (the one-launch-per-step cross-check kernel and the host emulator)
 template <int D, class LD, int PITCH>
-PDEOP_HD void gs_elem(const LevelDev& L, const int* __restrict__ rowbase, const double* __restrict__ T,
-                      const double* __restrict__ coef, const double* __restrict__ dinv,
-                      const double* __restrict__ b, double* x, int w) {
+PDEOP_HD void gs_fin_elem(const LevelDev& L, const int* __restrict__ rowbase, const double* __restrict__ T,
+                          const double* __restrict__ coef, const double* __restrict__ dinv, double* x, int w, int i0,
+                          int i1, int i2, bool eq, double r[1 + 2 * D]) {
+    FinLoads<D> f;
+    gs_fin_load<D, LD>(L, rowbase, coef, dinv, x, w, i0, i1, i2, eq, f);
+    PDEOP_LOAD_FENCE();
+    gs_fin_compute<D, PITCH>(L, T, x, w, i0, i1, i2, f, r);
+}
+
+// Both halves back to back, coordinates (L.coord[w]) supplied by the caller.  (Measured and dropped for the unsplit
+// kernel: issuing the finishing half's loads before the last gather axis is consumed spills -- 65 doubles live --,
+// and pulling them into L2 with prefetch.global.L2 is slower on the fine level, 3.05 vs 2.83 ms per call.)
+template <int D, class LD, int PITCH>
+PDEOP_HD void gs_elem_cf(const LevelDev& L, const int* __restrict__ rowbase, const double* __restrict__ T,
+                         const double* __restrict__ coef, const double* __restrict__ dinv,
+                         const double* __restrict__ b, double* x, int w, int cf) {
     int i0, i1, i2;
-    const int cf = L.coord[w];
     unpack_coord(cf, i0, i1, i2);
     double r[1 + 2 * D];
     gs_pre_elem<D, LD, PITCH>(L, rowbase, T, b, x, w, i0, i1, i2, r);
     gs_fin_elem<D, LD, PITCH>(L, rowbase, T, coef, dinv, x, w, i0, i1, i2, coord_eq(cf), r);
+}
+
+// (the one-launch-per-step cross-check kernel and the host emulator)
+template <int D, class LD, int PITCH>
+PDEOP_HD void gs_elem(const LevelDev& L, const int* __restrict__ rowbase, const double* __restrict__ T,
+                      const double* __restrict__ coef, const double* __restrict__ dinv,
+                      const double* __restrict__ b, double* x, int w) {
+    gs_elem_cf<D, LD, PITCH>(L, rowbase, T, coef, dinv, b, x, w, L.coord[w]);
 }
 
 // ------------------------------------------------------------------------------------------------
