@@ -130,6 +130,14 @@ int pdeop_fgmres(pdeop_plan* plan, const pdeop_solver_cfg* cfg, int back, const 
  * Categories: 0 GS fine level, 1 GS coarser levels, 2 K-apply/residual fine, 3 K-apply coarser, 4 grid
  * transfer, 5 coarsest triangular solves, 6 coarsest factorisation, 7 Krylov vector kernels, 8 set-up,
  * 9 gradients, 10 layout conversion. */
+/* Kernel-variant switches for A/B tests and profiling (no reference counterpart; defaults are the production
+ * choice and can also be preset through the environment variables PDEOP_GS_PIPE / PDEOP_CHAIN):
+ *   key 0 "gs_pipe": 0 unsplit cluster Gauss-Seidel kernel on every level, 1 software-pipelined kernel on every
+ *                    level, 2 (default) pipelined kernel on the latency-bound levels only
+ *   key 1 "chain"  : 1 (default) persistent chain kernels for the coarsest triangular solves where they apply,
+ *                    0 one launch per block row.  Takes effect at the next operator set-up.
+ * Returns 0, or 1 for an unknown key. */
+int pdeop_set_tuning(int key, int value);
 void pdeop_profile_enable(int on);
 int pdeop_profile_collect(double* ms_per_category, long long* count_per_category, int ncat);
 long long pdeop_launch_count(void);

@@ -31,6 +31,7 @@ EXPORTS = [
     "pdeop_plan_create", "pdeop_plan_destroy", "pdeop_plan_query", "pdeop_last_error", "pdeop_backend_name",
     "pdeop_mg_forward", "pdeop_mg_backward", "pdeop_dense_forward", "pdeop_dense_backward", "pdeop_mg_setup",
     "pdeop_stage", "pdeop_fgmres", "pdeop_profile_enable", "pdeop_profile_collect", "pdeop_launch_count",
+    "pdeop_set_tuning",
 ]
 
 PROFILE_CATEGORIES = ["gs_fine", "gs_coarse", "apply_fine", "apply_coarse", "transfer", "coarse_solve", "factor",
@@ -96,6 +97,12 @@ class PdeopLibrary:
 
     def launch_count(self):
         return int(self.dll.pdeop_launch_count())
+
+    def set_tuning(self, key, value):
+        """Kernel-variant switch (pdeop.h: pdeop_set_tuning); key 'gs_pipe' or 'chain'."""
+        k = {"gs_pipe": 0, "chain": 1}[key]
+        if self.dll.pdeop_set_tuning(k, int(value)) != 0:
+            raise PdeopError("unknown tuning key")
 
     def check(self, rc):
         if rc != 0:

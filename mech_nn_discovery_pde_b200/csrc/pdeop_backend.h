@@ -23,6 +23,7 @@ void be_event_destroy(void* ev);
 void be_event_record(void* ev, stream_t st);
 float be_event_elapsed_ms(void* start, void* stop);  // waits for `stop`
 long long be_launch_count();
+int be_set_tuning(int key, int value);   // see pdeop_set_tuning
 
 void be_build_tables(stream_t st, const LevelDev& L, int B, const double* cv, const double* fv, const double* bv,
                      double* T);

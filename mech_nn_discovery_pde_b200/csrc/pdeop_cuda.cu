@@ -1303,6 +1303,19 @@ static bool chain_enabled() {
     return g_chain != 0;
 }
 
+int be_set_tuning(int key, int value) {
+    if (key == 0) {
+        gs_tuning();
+        g_gs_pipe = value;
+        return 0;
+    }
+    if (key == 1) {
+        g_chain = value ? 1 : 0;
+        return 0;
+    }
+    return 1;
+}
+
 void be_cholesky(stream_t st, int B, int n, int bw, double* Kd, double* Linv, FgmresState* state) {
     cudaStream_t s = (cudaStream_t)st;
     const size_t strideA = (size_t)n * n;

@@ -60,6 +60,7 @@ extern "C" int pdeop_profile_collect(double* ms, long long* counts, int ncat) {
     return PC_COUNT;
 }
 extern "C" long long pdeop_launch_count(void) { return be_launch_count(); }
+extern "C" int pdeop_set_tuning(int key, int value) { return be_set_tuning(key, value); }
 
 static int fail(const std::string& msg) {
     g_err = msg;

@@ -286,3 +286,62 @@ def test_gl_scaling_grid_smoke(lib):
 def test_fgmres_control_flow(lib):
     from tests.test_emu_structure import check_fgmres_control_flow
     check_fgmres_control_flow(lib, "cuda:0")
+
+
+def test_gs_kernel_variants_bit_identical(lib):
+    """The three Gauss-Seidel kernels (unsplit cluster kernel, software-pipelined kernel with the split cluster
+    barrier, one launch per hyperplane step) run the same canonical arithmetic: identical bits, on a level with one
+    point per thread and step and on one with several rounds (register + global stash paths of the pipelined kernel)."""
+    iv = IV_LISTS["gl"]
+    for dims, B, n_grid in (((8, 16, 16), 3, 2), ((32, 32, 32), 2, 3)):
+        G, M = int(np.prod(dims)), 7
+        rng = np.random.default_rng(17)
+        coeffs = np.zeros((B, G, M))
+        coeffs[..., 0] = 0.1 * rng.standard_normal((B, G))
+        coeffs[..., 1] = 1.0
+        coeffs[..., 5] = -1.0
+        coeffs[..., 6] = -0.7
+        steps = [np.full((B, n - 1), h) + 0.01 * rng.random((B, n - 1)) for n, h in zip(dims, (0.1, 0.39, 0.41))]
+        sr = StageRunner(lib, "cuda:0", dims, iv, B, n_grid, False, coeffs, steps)
+        n = B * G * M
+        b, x0 = rng.standard_normal(n), rng.standard_normal(n)
+        outs = {}
+        try:
+            for mode in (0, 1):
+                lib.set_tuning("gs_pipe", mode)
+                outs[mode] = sr.stage(_lib.STAGE_GS, 0, b, x0, count=5)
+        finally:
+            lib.set_tuning("gs_pipe", 2)
+        step_kernel = sr.stage(_lib.STAGE_GS, 0, b, x0, count=5, gs_variant=1)
+        assert np.array_equal(outs[0], outs[1])
+        assert np.array_equal(outs[0], step_kernel)
+
+
+def test_chain_solver_matches_block_row_solver(lib):
+    """Coarsest-level triangular solves: the persistent chain kernels (block-scaled band, TMA + mbarrier pipeline,
+    DSMEM exchange) against the one-launch-per-block-row path, on the same factor, and the residual of the solve.
+    8x8x8 coarsest grid: n = 3584 = 28 block rows, half-bandwidth 1798 (the band structure of the BASELINE grid)."""
+    iv = IV_LISTS["gl"]
+    dims, B, n_grid = (8, 16, 16), 3, 2
+    G, M = int(np.prod(dims)), 7
+    rng = np.random.default_rng(23)
+    coeffs = np.zeros((B, G, M))
+    coeffs[..., 0] = 0.1 * rng.standard_normal((B, G))
+    coeffs[..., 1] = 1.0
+    coeffs[..., 5] = -1.0
+    coeffs[..., 6] = -1.0
+    steps = [np.full((B, n - 1), h) for n, h in zip(dims, (0.1, 0.39, 0.39))]
+    sols = {}
+    try:
+        for mode in (1, 0):
+            lib.set_tuning("chain", mode)   # read at operator set-up
+            sr = StageRunner(lib, "cuda:0", dims, iv, B, n_grid, False, coeffs, steps)
+            nc = sr.level_n(1)
+            rhs = np.random.default_rng(5).standard_normal(B * nc)
+            sols[mode] = sr.stage(_lib.STAGE_COARSE_SOLVE, 1, rhs)
+            if mode == 1:
+                res = rhs - sr.stage(_lib.STAGE_APPLY_K, 1, sols[mode])
+                assert np.linalg.norm(res) < 1e-5 * np.linalg.norm(rhs)
+    finally:
+        lib.set_tuning("chain", 1)
+    assert rel(sols[1], sols[0]) < 1e-10
