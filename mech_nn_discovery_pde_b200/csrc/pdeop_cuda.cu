@@ -165,6 +165,7 @@ void be_atb(stream_t st, const LevelDev& L, int B, const double* coef, const dou
     }
 }
 
+// (3 CTAs per SM -- __launch_bounds__(kThreads, 3), 80 registers -- spills 400 bytes per thread: not used)
 template <int D>
 __global__ void __launch_bounds__(kThreads) k_apply(LevelDev L, const double* __restrict__ T,
                                                     const double* __restrict__ coef, const double* __restrict__ x,
