@@ -872,6 +872,14 @@ static void launch_dots(cudaStream_t s, size_t n, const double* V, size_t ldv, i
                         double* partial, const int* done) {
     const int nb = reduce_blocks(n);
     int k0 = 0;
+    // up to 10 vectors (the default restart length) in one pass over w
+#define PDEOP_DOTS_CASE(KK) \
+    case KK: k_dots<KK><<<nb, kThreads, 0, s>>>(n, V, ldv, 0, w, partial, done); k0 = nv; PDEOP_COUNT(1); break;
+    switch (nv) {
+        PDEOP_DOTS_CASE(3) PDEOP_DOTS_CASE(5) PDEOP_DOTS_CASE(6) PDEOP_DOTS_CASE(7) PDEOP_DOTS_CASE(9) PDEOP_DOTS_CASE(10)
+        default: break;
+    }
+#undef PDEOP_DOTS_CASE
     while (k0 < nv) {
         const int rem = nv - k0;
         if (rem >= 8) { k_dots<8><<<nb, kThreads, 0, s>>>(n, V, ldv, k0, w, partial, done); k0 += 8; }
@@ -937,6 +945,8 @@ void be_fg_first(stream_t st, size_t n, const double* r, double* V0, FgmresState
 }
 
 // w -= sum_{k<=j} h_k V_k with h_k re-summed from the dot partials; block partials of ||w||^2 -> area 1
+// KC = j + 1 at compile time (loads of all vectors in flight together), KC = 0: run-time loop
+template <int KC>
 __global__ void __launch_bounds__(kThreads) k_axpy_norm(size_t n, int j, int restart, const double* __restrict__ V,
                                                         double* __restrict__ w, FgmresState* s, int nblk) {
     if (s->done) return;
@@ -955,7 +965,15 @@ __global__ void __launch_bounds__(kThreads) k_axpy_norm(size_t n, int j, int res
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         double wi = w[i];
-        for (int k = 0; k <= j; ++k) wi -= h[k] * V[(size_t)k * n + i];
+        if (KC > 0) {
+            double vk[KC > 0 ? KC : 1];
+#pragma unroll
+            for (int k = 0; k < KC; ++k) vk[k] = V[(size_t)k * n + i];
+#pragma unroll
+            for (int k = 0; k < KC; ++k) wi -= h[k] * vk[k];
+        } else {
+            for (int k = 0; k <= j; ++k) wi -= h[k] * V[(size_t)k * n + i];
+        }
         w[i] = wi;
         acc += wi * wi;
     }
@@ -987,7 +1005,13 @@ void be_fg_cgs(stream_t st, size_t n, int j, int restart, double* V, double* w, 
     cudaStream_t cs = (cudaStream_t)st;
     const int nb = reduce_blocks(n);
     launch_dots(cs, n, V, n, j + 1, w, state_partials(s, 0), &s->done);
-    k_axpy_norm<<<nb, kThreads, 0, cs>>>(n, j, restart, V, w, s, nb);
+#define PDEOP_AXPY_CASE(KK) case KK: k_axpy_norm<KK><<<nb, kThreads, 0, cs>>>(n, j, restart, V, w, s, nb); break;
+    switch (j + 1) {
+        PDEOP_AXPY_CASE(1) PDEOP_AXPY_CASE(2) PDEOP_AXPY_CASE(3) PDEOP_AXPY_CASE(4) PDEOP_AXPY_CASE(5)
+        PDEOP_AXPY_CASE(6) PDEOP_AXPY_CASE(7) PDEOP_AXPY_CASE(8) PDEOP_AXPY_CASE(9) PDEOP_AXPY_CASE(10)
+        default: k_axpy_norm<0><<<nb, kThreads, 0, cs>>>(n, j, restart, V, w, s, nb); break;
+    }
+#undef PDEOP_AXPY_CASE
     k_scale_next<<<(j + 1 < restart) ? nb : 1, kThreads, 0, cs>>>(n, j, restart, V, w, s, nb);
     PDEOP_COUNT(2);
     PDEOP_LAUNCH_CHECK();

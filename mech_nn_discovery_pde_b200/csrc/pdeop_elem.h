@@ -593,14 +593,39 @@ PDEOP_HD void interp_elem(const LevelDev& Li, const LevelDev& Lo, int C, const d
     interp_axis(i0, Li.N[0], Lo.N[0], l[0], h[0], w0[0], w1[0]);
     interp_axis(i1, Li.N[1], Lo.N[1], l[1], h[1], w0[1], w1[1]);
     interp_axis(i2, Li.N[2], Lo.N[2], l[2], h[2], w0[2], w1[2]);
-    const int p000 = wave_pos(Li, l[0], l[1], l[2]), p001 = wave_pos(Li, l[0], l[1], h[2]);
-    const int p010 = wave_pos(Li, l[0], h[1], l[2]), p011 = wave_pos(Li, l[0], h[1], h[2]);
-    const int p100 = wave_pos(Li, h[0], l[1], l[2]), p101 = wave_pos(Li, h[0], l[1], h[2]);
-    const int p110 = wave_pos(Li, h[0], h[1], l[2]), p111 = wave_pos(Li, h[0], h[1], h[2]);
+    // Corners with an exactly zero weight are not read (l1 == 0 means l0 == 1: w0*a + 0*b == w0*a bit for bit).  An
+    // axis that is not coarsened (downsample_first=False keeps the time axis) always has l1 == 0: half the gathers.
+    const bool z0 = w1[0] != 0.0, z1 = w1[1] != 0.0, z2 = w1[2] != 0.0;
+    const int p000 = wave_pos(Li, l[0], l[1], l[2]);
+    const int p001 = z2 ? wave_pos(Li, l[0], l[1], h[2]) : p000;
+    const int p010 = z1 ? wave_pos(Li, l[0], h[1], l[2]) : p000;
+    const int p011 = (z1 && z2) ? wave_pos(Li, l[0], h[1], h[2]) : p000;
+    const int p100 = z0 ? wave_pos(Li, h[0], l[1], l[2]) : p000;
+    const int p101 = (z0 && z2) ? wave_pos(Li, h[0], l[1], h[2]) : p000;
+    const int p110 = (z0 && z1) ? wave_pos(Li, h[0], h[1], l[2]) : p000;
+    const int p111 = (z0 && z1 && z2) ? wave_pos(Li, h[0], h[1], h[2]) : p000;
     for (int m = 0; m < C; ++m) {
         const double* __restrict__ s = in + (size_t)m * Li.G;
-        const double v = w0[0] * (w0[1] * (w0[2] * s[p000] + w1[2] * s[p001]) + w1[1] * (w0[2] * s[p010] + w1[2] * s[p011])) +
-                         w1[0] * (w0[1] * (w0[2] * s[p100] + w1[2] * s[p101]) + w1[1] * (w0[2] * s[p110] + w1[2] * s[p111]));
+        double a0 = w0[2] * s[p000];
+        if (z2) a0 += w1[2] * s[p001];
+        double lo = w0[1] * a0;
+        if (z1) {
+            double a1 = w0[2] * s[p010];
+            if (z2) a1 += w1[2] * s[p011];
+            lo += w1[1] * a1;
+        }
+        double v = w0[0] * lo;
+        if (z0) {
+            double b0 = w0[2] * s[p100];
+            if (z2) b0 += w1[2] * s[p101];
+            double hi = w0[1] * b0;
+            if (z1) {
+                double b1 = w0[2] * s[p110];
+                if (z2) b1 += w1[2] * s[p111];
+                hi += w1[1] * b1;
+            }
+            v += w1[0] * hi;
+        }
         const size_t k = (size_t)m * Lo.G + wo;
         out[k] = add ? out[k] + v : v;
     }
