@@ -1536,7 +1536,8 @@ constexpr int kChainWarps = 8;       // consumer warps
 constexpr int kChainDepth = 3;       // stages per consumer warp (each warp owns its stages: a parity wait is only
                                      // meaningful for a waiter that observes every phase of its barrier in order)
 constexpr int kChainStages = kChainWarps * kChainDepth;
-constexpr int kChainCH = 848;        // doubles per stage (one chunk of a row's old part): 24 stages = 159 KB in flight
+constexpr int kChainCHMax = 896;     // doubles per stage (one chunk of a row's old part): 24 stages = 168 KB in flight;
+                                     // the launcher picks the largest multiple of 32 <= this that fits shared memory
 constexpr int kChainThreads = (kChainWarps + 2) * 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -1642,7 +1643,7 @@ __device__ __forceinline__ ChainRow chain_row(int dir, int n, int nblk, int pw, 
     return r;
 }
 
-__global__ void __launch_bounds__(kChainThreads, 1) k_band_chain(int dir, int n, int nblk, int pw, int pwt, int nw,
+__global__ void __launch_bounds__(kChainThreads, 1) k_band_chain(int dir, int n, int nblk, int pw, int pwt, int nw, int ch,
                                                                 const double* __restrict__ W,
                                                                 const double* __restrict__ vin,
                                                                 double* __restrict__ vout, const int* done) {
@@ -1653,8 +1654,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_band_chain(int dir, int n,
     const int ib = blockIdx.x / kChainCta;
     double* newbuf = reinterpret_cast<double*>(ch_smem);                  // [kChainRows][kSolveBlk]
     constexpr int ns = kChainStages;
-    double* ring = newbuf + kChainRows * kSolveBlk;                       // [kChainStages][kChainCH]
-    double* win = ring + (size_t)ns * kChainCH;                           // [nw][kSolveBlk]
+    double* ring = newbuf + kChainRows * kSolveBlk;                       // [kChainStages][ch]
+    double* win = ring + (size_t)ns * ch;                           // [nw][kSolveBlk]
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(win + (size_t)nw * kSolveBlk);
     // bars: full[ns] | empty[ns] | full_new | empty_new | ready[2]
     const uint32_t b_full = smem_u32(bars), b_empty = smem_u32(bars + ns);
@@ -1694,18 +1695,18 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_band_chain(int dir, int n,
                 const int k = dir == 0 ? s : nblk - 1 - s;
                 const int gl = k * kSolveBlk + q * kChainRows;
                 const ChainRow last = chain_row(dir, n, nblk, pw, pwt, Wi, k, s, min(gl + kChainRows - 1, n - 1));
-                const int nch = (last.old_len + kChainCH - 1) / kChainCH;
+                const int nch = (last.old_len + ch - 1) / ch;
                 for (int m = 0; m < kChainRows / kChainWarps; ++m) {
                     const ChainRow r = chain_row(dir, n, nblk, pw, pwt, Wi, k, s, gl + wv + kChainWarps * m);
                     for (int c = 0; c < nch; ++c, ++lq) {
                         const unsigned stage = (unsigned)wv * kChainDepth + lq % kChainDepth;
                         const unsigned par = (lq / kChainDepth) & 1u;
                         mbar_wait(b_empty + 8 * stage, par ^ 1u);
-                        int len = r.old_len - c * kChainCH;
-                        if (len > kChainCH) len = kChainCH;
+                        int len = r.old_len - c * ch;
+                        if (len > ch) len = ch;
                         if (len > 0) {
                             mbar_expect_tx(b_full + 8 * stage, (uint32_t)len * 8u);
-                            bulk_g2s(smem_u32(ring + (size_t)stage * kChainCH), r.old_src + (size_t)c * kChainCH,
+                            bulk_g2s(smem_u32(ring + (size_t)stage * ch), r.old_src + (size_t)c * ch,
                                      (uint32_t)len * 8u, b_full + 8 * stage);
                         } else {
                             mbar_arrive(b_full + 8 * stage);
@@ -1763,7 +1764,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_band_chain(int dir, int n,
             int nch = 0;
             if (s > 0) {
                 const ChainRow last = chain_row(dir, n, nblk, pw, pwt, Wi, k, s, min(gl + kChainRows - 1, n - 1));
-                nch = (last.old_len + kChainCH - 1) / kChainCH;
+                nch = (last.old_len + ch - 1) / ch;
                 const int k0 = k * kSolveBlk;
                 const int v0 = dir == 0 ? (k0 - pw > 0 ? k0 - pw : 0) : (k + 2) * kSolveBlk;
                 // old phase: needs blocks solved two or more steps ago, all delivered before the previous new phase
@@ -1776,11 +1777,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_band_chain(int dir, int n,
                         const unsigned stage = (unsigned)wv * kChainDepth + lq % kChainDepth;
                         const unsigned par = (lq / kChainDepth) & 1u;
                         mbar_wait(b_full + 8 * stage, par);
-                        int len = r.old_len - c * kChainCH;
-                        if (len > kChainCH) len = kChainCH;
+                        int len = r.old_len - c * ch;
+                        if (len > ch) len = ch;
                         if (len > 0) {
-                            const double* wc = ring + (size_t)stage * kChainCH;
-                            const int gv = v0 + c * kChainCH + 2 * lane;   // vector index of this lane's first pair
+                            const double* wc = ring + (size_t)stage * ch;
+                            const int gv = v0 + c * ch + 2 * lane;   // vector index of this lane's first pair
                             int slot = (gv / kSolveBlk) % nw, off = gv % kSolveBlk;
                             double a = acc[m];
                             for (int e = 2 * lane; e < len; e += 64) {
@@ -1870,8 +1871,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_band_chain(int dir, int n,
     cluster.sync();   // no CTA leaves while others may still store into its window or arrive on its barriers
 }
 
-static size_t chain_smem_bytes(int nw) {
-    return ((size_t)kChainRows * kSolveBlk + (size_t)kChainStages * kChainCH + (size_t)nw * kSolveBlk) * sizeof(double) +
+static size_t chain_smem_bytes(int nw, int ch) {
+    return ((size_t)kChainRows * kSolveBlk + (size_t)kChainStages * ch + (size_t)nw * kSolveBlk) * sizeof(double) +
            (size_t)(2 * kChainStages + 4) * 8;
 }
 
@@ -1900,7 +1901,9 @@ __global__ void __launch_bounds__(256) k_blk_mv_all(int n, const double* __restr
 static void launch_chain(cudaStream_t s, int dir, int B, int n, const ChainLayout& cl, const double* W, const double* vin,
                          double* vout, const int* done) {
     const int nw = cl.nbmax + 1;
-    const size_t smem = chain_smem_bytes(nw);
+    int ch = kChainCHMax;
+    while (ch > 64 && chain_smem_bytes(nw, ch) > (size_t)227 * 1024) ch -= 32;
+    const size_t smem = chain_smem_bytes(nw, ch);
     static size_t set_for = 0;
     if (smem > set_for) {
         note(cudaFuncSetAttribute(k_band_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1919,7 +1922,7 @@ static void launch_chain(cudaStream_t s, int dir, int B, int n, const ChainLayou
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    note(cudaLaunchKernelEx(&cfg, k_band_chain, dir, n, cl.nblk, cl.pw, cl.pwt, nw, W, vin, vout, done));
+    note(cudaLaunchKernelEx(&cfg, k_band_chain, dir, n, cl.nblk, cl.pw, cl.pwt, nw, ch, W, vin, vout, done));
     PDEOP_COUNT(1);
 }
 
