@@ -181,6 +181,7 @@ def run_ours(args, wl):
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch or wl["batch"]
     dims = wl["dims"]
