@@ -1138,8 +1138,7 @@ __global__ void __launch_bounds__(128) k_chol_trsm(int n, double* A, size_t stri
 }
 
 // C[i][j] -= sum_{t in [p0,p1)} A[i][t] A[j][t]   for i in [r0,r1), j in [c0,c1), i >= j
-// Tensor-core path for fp64: mma.sync.m8n8k4.f64 (DMMA; fp64 has no tcgen05 kind).  128x128 tile per CTA, 8 warps
-// as 4 (rows) x 2 (columns), each warp a 32x64 sub-tile = 4x8 m8n8 accumulator tiles (64 doubles per lane).
+// Tensor-core path for fp64: mma.sync.m8n8k4.f64 (DMMA; fp64 has no tcgen05 kind).  128x128 tile per CTA.
 // Both operands come from the same row-major panel: A fragment = P[i][k], B fragment (column-major k x n) = P[j][k].
 // Shared tiles are [row][k] with a 20-double pitch: a half-warp's 64-bit fragment loads hit 32 distinct banks.
 // The next K-chunk is prefetched into registers while the current one is multiplied.
@@ -1153,10 +1152,19 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                  : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(256, 1) k_syrk(int n, double* A, size_t strideA, int r0, int r1, int c0, int c1,
-                                                 int p0, int p1) {
+// 16 warps as 4 (rows) x 4 (columns), each a 32x32 sub-tile = 4x4 m8n8 accumulator tiles (32 doubles per lane):
+// with 8 warps and 64 accumulators per lane (206 registers) only 2 warps per scheduler were resident and the tensor
+// pipe idled 50 % of the time behind their global-load and fixed-latency stalls (profiles/r1_syrk_dmma_tensor_pipe.csv).
+constexpr int kSyrkThreads = 512;
+// bw: half-bandwidth of the factor.  Row i of L is zero left of column i - bw, so a tile whose first row is i0 only
+// needs the panel columns t >= i0 - bw: the lowest tile rows of a trailing update skip most of the panel depth
+// (17 % of the tile work at bw = 1798, depth 256; the skipped products are exact zeros).
+__global__ void __launch_bounds__(kSyrkThreads, 1) k_syrk(int n, double* A, size_t strideA, int r0, int r1, int c0, int c1,
+                                                          int p0, int p1, int bw) {
     const int i0 = r0 + blockIdx.x * kSyrkT, j0 = c0 + blockIdx.y * kSyrkT;
     if (i0 + kSyrkT - 1 < j0) return;   // tile entirely above the diagonal
+    if (i0 - bw > p0) p0 += (i0 - bw - p0) / kSyrkK * kSyrkK;
+    if (p0 >= p1) return;
     __shared__ double As[kSyrkT][kSyrkLd];
     __shared__ double Bs[kSyrkT][kSyrkLd];
     double* Ab = A + (size_t)blockIdx.z * strideA;
@@ -1164,32 +1172,32 @@ __global__ void __launch_bounds__(256, 1) k_syrk(int n, double* A, size_t stride
     const int warp = tid >> 5, lane = tid & 31;
     const int wi = warp & 3, wj = warp >> 2;
     const int gid = lane >> 2, tig = lane & 3;
-    const int lr = tid >> 1, lk = (tid & 1) * 8;   // loader: row lr of the tile, 8 consecutive k
+    const int lr = tid >> 2, lk = (tid & 3) * 4;   // loader: row lr of the tile, 4 consecutive k
     const bool arow = i0 + lr < r1, brow = j0 + lr < c1;
     const double* ap = Ab + (size_t)(i0 + lr) * n + lk;
     const double* bp = Ab + (size_t)(j0 + lr) * n + lk;
-    double acc[4][8][2];
+    double acc[4][4][2];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 8; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-    double ra[8], rb[8];
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    double ra[4], rb[4];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < 4; ++q) {
         const int k = p0 + lk + q;
         ra[q] = (arow && k < p1) ? ap[p0 + q] : 0.0;
         rb[q] = (brow && k < p1) ? bp[p0 + q] : 0.0;
     }
     for (int kk = p0; kk < p1; kk += kSyrkK) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 4; ++q) {
             As[lr][lk + q] = ra[q];
             Bs[lr][lk + q] = rb[q];
         }
         __syncthreads();
         if (kk + kSyrkK < p1) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < 4; ++q) {
                 const int k = kk + kSyrkK + lk + q;
                 ra[q] = (arow && k < p1) ? ap[kk + kSyrkK + q] : 0.0;
                 rb[q] = (brow && k < p1) ? bp[kk + kSyrkK + q] : 0.0;
@@ -1197,15 +1205,15 @@ __global__ void __launch_bounds__(256, 1) k_syrk(int n, double* A, size_t stride
         }
 #pragma unroll
         for (int ks = 0; ks < kSyrkK / 4; ++ks) {
-            double af[4], bf[8];
+            double af[4], bf[4];
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt) af[mt] = As[wi * 32 + mt * 8 + gid][ks * 4 + tig];
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) bf[nt] = Bs[wj * 64 + nt * 8 + gid][ks * 4 + tig];
+            for (int nt = 0; nt < 4; ++nt) bf[nt] = Bs[wj * 32 + nt * 8 + gid][ks * 4 + tig];
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-                for (int nt = 0; nt < 8; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+                for (int nt = 0; nt < 4; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
         }
         __syncthreads();
     }
@@ -1214,20 +1222,21 @@ __global__ void __launch_bounds__(256, 1) k_syrk(int n, double* A, size_t stride
         const int i = i0 + wi * 32 + mt * 8 + gid;
         if (i >= r1) continue;
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
+        for (int nt = 0; nt < 4; ++nt) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int j = j0 + wj * 64 + nt * 8 + 2 * tig + e;
+                const int j = j0 + wj * 32 + nt * 8 + 2 * tig + e;
                 if (j < c1 && i >= j) Ab[(size_t)i * n + j] -= acc[mt][nt][e];
             }
         }
     }
 }
 
-static void launch_syrk(cudaStream_t s, int B, int n, double* A, int r0, int r1, int c0, int c1, int p0, int p1) {
+static void launch_syrk(cudaStream_t s, int B, int n, double* A, int r0, int r1, int c0, int c1, int p0, int p1,
+                        int bw) {
     if (r0 >= r1 || c0 >= c1 || p0 >= p1) return;
     dim3 grid(cdiv(r1 - r0, kSyrkT), cdiv(c1 - c0, kSyrkT), B);
-    k_syrk<<<grid, 256, 0, s>>>(n, A, (size_t)n * n, r0, r1, c0, c1, p0, p1);
+    k_syrk<<<grid, kSyrkThreads, 0, s>>>(n, A, (size_t)n * n, r0, r1, c0, c1, p0, p1, bw);
     PDEOP_COUNT(1);
 }
 
@@ -1358,13 +1367,13 @@ void be_cholesky(stream_t st, int B, int n, int bw, double* Kd, double* Linv, Fg
                 k_chol_trsm<<<dim3(cdiv(r1 - k0 - nb, 128), B), 128, 0, s>>>(n, Kd, strideA, k0, nb, r1);
                 PDEOP_COUNT(1);
                 // rest of the outer panel: columns [k0+nb, K1)
-                launch_syrk(s, B, n, Kd, k0 + nb, r1, k0 + nb, K1 < r1 ? K1 : r1, k0, k0 + nb);
+                launch_syrk(s, B, n, Kd, k0 + nb, r1, k0 + nb, K1 < r1 ? K1 : r1, k0, k0 + nb, bw);
             }
         }
         // trailing matrix: columns [K1, K1+bw), depth kOuter
         const long long lim = (long long)K1 + bw;
         const int r1 = lim < n ? (int)lim : n;
-        launch_syrk(s, B, n, Kd, K1, r1, K1, r1, K0, K1);
+        launch_syrk(s, B, n, Kd, K1, r1, K1, r1, K0, K1, bw);
     }
     const int nblk = (n + kSolveBlk - 1) / kSolveBlk;
     k_trtri<<<dim3(nblk, B), kSolveBlk, 0, s>>>(n, Kd, strideA, Linv, nblk);
