@@ -1159,28 +1159,32 @@ constexpr int kSyrkThreads = 512;
 // bw: half-bandwidth of the factor.  Row i of L is zero left of column i - bw, so a tile whose first row is i0 only
 // needs the panel columns t >= i0 - bw: the lowest tile rows of a trailing update skip most of the panel depth
 // (17 % of the tile work at bw = 1798, depth 256; the skipped products are exact zeros).
+// TN: tile width.  128: 16 warps as 4 x 4, each a 32x32 sub-tile; 32 (block-column updates of the left-looking
+// panel factorisation): 16 warps as 16 x 1, each 8 rows x 32 columns.
+template <int TN>
 __global__ void __launch_bounds__(kSyrkThreads, 1) k_syrk(int n, double* A, size_t strideA, int r0, int r1, int c0, int c1,
                                                           int p0, int p1, int bw) {
-    const int i0 = r0 + blockIdx.x * kSyrkT, j0 = c0 + blockIdx.y * kSyrkT;
+    constexpr int MT = TN == 128 ? 4 : 1, NT = 4;
+    const int i0 = r0 + blockIdx.x * kSyrkT, j0 = c0 + blockIdx.y * TN;
     if (i0 + kSyrkT - 1 < j0) return;   // tile entirely above the diagonal
     if (i0 - bw > p0) p0 += (i0 - bw - p0) / kSyrkK * kSyrkK;
     if (p0 >= p1) return;
     __shared__ double As[kSyrkT][kSyrkLd];
-    __shared__ double Bs[kSyrkT][kSyrkLd];
+    __shared__ double Bs[TN][kSyrkLd];
     double* Ab = A + (size_t)blockIdx.z * strideA;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int wi = warp & 3, wj = warp >> 2;
+    const int rbase = TN == 128 ? (warp & 3) * 32 : warp * 8, cbase = TN == 128 ? (warp >> 2) * 32 : 0;
     const int gid = lane >> 2, tig = lane & 3;
     const int lr = tid >> 2, lk = (tid & 3) * 4;   // loader: row lr of the tile, 4 consecutive k
-    const bool arow = i0 + lr < r1, brow = j0 + lr < c1;
+    const bool arow = i0 + lr < r1, brow = lr < TN && j0 + lr < c1;
     const double* ap = Ab + (size_t)(i0 + lr) * n + lk;
-    const double* bp = Ab + (size_t)(j0 + lr) * n + lk;
-    double acc[4][4][2];
+    const double* bp = Ab + (size_t)(j0 + (lr < TN ? lr : 0)) * n + lk;
+    double acc[MT][NT][2];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < MT; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+        for (int b = 0; b < NT; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
     double ra[4], rb[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -1192,7 +1196,7 @@ __global__ void __launch_bounds__(kSyrkThreads, 1) k_syrk(int n, double* A, size
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             As[lr][lk + q] = ra[q];
-            Bs[lr][lk + q] = rb[q];
+            if (lr < TN) Bs[lr][lk + q] = rb[q];
         }
         __syncthreads();
         if (kk + kSyrkK < p1) {
@@ -1205,27 +1209,27 @@ __global__ void __launch_bounds__(kSyrkThreads, 1) k_syrk(int n, double* A, size
         }
 #pragma unroll
         for (int ks = 0; ks < kSyrkK / 4; ++ks) {
-            double af[4], bf[4];
+            double af[MT], bf[NT];
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt) af[mt] = As[wi * 32 + mt * 8 + gid][ks * 4 + tig];
+            for (int mt = 0; mt < MT; ++mt) af[mt] = As[rbase + mt * 8 + gid][ks * 4 + tig];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) bf[nt] = Bs[wj * 32 + nt * 8 + gid][ks * 4 + tig];
+            for (int nt = 0; nt < NT; ++nt) bf[nt] = Bs[cbase + nt * 8 + gid][ks * 4 + tig];
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt)
+            for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+                for (int nt = 0; nt < NT; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt) {
-        const int i = i0 + wi * 32 + mt * 8 + gid;
+    for (int mt = 0; mt < MT; ++mt) {
+        const int i = i0 + rbase + mt * 8 + gid;
         if (i >= r1) continue;
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
+        for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int j = j0 + wj * 32 + nt * 8 + 2 * tig + e;
+                const int j = j0 + cbase + nt * 8 + 2 * tig + e;
                 if (j < c1 && i >= j) Ab[(size_t)i * n + j] -= acc[mt][nt][e];
             }
         }
@@ -1235,8 +1239,13 @@ __global__ void __launch_bounds__(kSyrkThreads, 1) k_syrk(int n, double* A, size
 static void launch_syrk(cudaStream_t s, int B, int n, double* A, int r0, int r1, int c0, int c1, int p0, int p1,
                         int bw) {
     if (r0 >= r1 || c0 >= c1 || p0 >= p1) return;
-    dim3 grid(cdiv(r1 - r0, kSyrkT), cdiv(c1 - c0, kSyrkT), B);
-    k_syrk<<<grid, kSyrkThreads, 0, s>>>(n, A, (size_t)n * n, r0, r1, c0, c1, p0, p1, bw);
+    if (c1 - c0 <= 32) {
+        dim3 grid(cdiv(r1 - r0, kSyrkT), 1, B);
+        k_syrk<32><<<grid, kSyrkThreads, 0, s>>>(n, A, (size_t)n * n, r0, r1, c0, c1, p0, p1, bw);
+    } else {
+        dim3 grid(cdiv(r1 - r0, kSyrkT), cdiv(c1 - c0, kSyrkT), B);
+        k_syrk<128><<<grid, kSyrkThreads, 0, s>>>(n, A, (size_t)n * n, r0, r1, c0, c1, p0, p1, bw);
+    }
     PDEOP_COUNT(1);
 }
 
@@ -1359,15 +1368,17 @@ void be_cholesky(stream_t st, int B, int n, int bw, double* Kd, double* Linv, Fg
         const int K1 = K0 + kOuter < n ? K0 + kOuter : n;
         for (int k0 = K0; k0 < K1; k0 += kInner) {
             const int nb = k0 + kInner < K1 ? kInner : K1 - k0;
-            k_chol_diag<<<B, 256, 0, s>>>(n, Kd, strideA, k0, nb, state);
-            PDEOP_COUNT(1);
             const long long lim = (long long)k0 + nb + bw;
             const int r1 = lim < n ? (int)lim : n;
+            // left-looking inside the outer panel: bring block column k0 up to date with the panel columns
+            // factored so far (depth k0 - K0) just before it is factored -- every block column is read-modify-
+            // written once instead of once per earlier inner block
+            launch_syrk(s, B, n, Kd, k0, r1, k0, k0 + nb, K0, k0, bw);
+            k_chol_diag<<<B, 256, 0, s>>>(n, Kd, strideA, k0, nb, state);
+            PDEOP_COUNT(1);
             if (k0 + nb < r1) {
                 k_chol_trsm<<<dim3(cdiv(r1 - k0 - nb, 128), B), 128, 0, s>>>(n, Kd, strideA, k0, nb, r1);
                 PDEOP_COUNT(1);
-                // rest of the outer panel: columns [k0+nb, K1)
-                launch_syrk(s, B, n, Kd, k0 + nb, r1, k0 + nb, K1 < r1 ? K1 : r1, k0, k0 + nb, bw);
             }
         }
         // trailing matrix: columns [K1, K1+bw), depth kOuter
