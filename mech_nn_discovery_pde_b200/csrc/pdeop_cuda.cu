@@ -846,6 +846,11 @@ static inline int reduce_blocks(size_t n) {
 }
 
 // partial[(k0+k)*kReduceBlocks + blk] = sum_i V[(k0+k)*ldv + i] * w[i],  k < K
+// vectors of even length and stride on 16-byte boundaries can be streamed as double2
+__device__ __forceinline__ bool vec2_ok(size_t n, size_t ld, const void* a, const void* b) {
+    return (n % 2 == 0) && (ld % 2 == 0) && (((uintptr_t)a | (uintptr_t)b) % 16 == 0);
+}
+
 template <int K>
 __global__ void __launch_bounds__(kThreads) k_dots(size_t n, const double* __restrict__ V, size_t ldv, int k0,
                                                    const double* __restrict__ w, double* __restrict__ partial,
@@ -856,10 +861,24 @@ __global__ void __launch_bounds__(kThreads) k_dots(size_t n, const double* __res
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = 0.0;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const double wi = w[i];
+    if (vec2_ok(n, ldv, V, w)) {   // 16-byte loads: half the instructions, twice the contiguous bytes per warp and stream
+        const size_t n2 = n / 2, ld2 = ldv / 2;
+        const double2* __restrict__ w2 = reinterpret_cast<const double2*>(w);
+        const double2* __restrict__ V2 = reinterpret_cast<const double2*>(V);
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+            const double2 wi = w2[i];
+            double2 vk[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) acc[k] += V[(size_t)(k0 + k) * ldv + i] * wi;
+            for (int k = 0; k < K; ++k) vk[k] = V2[(size_t)(k0 + k) * ld2 + i];
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] += vk[k].x * wi.x + vk[k].y * wi.y;
+        }
+    } else {
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+            const double wi = w[i];
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] += V[(size_t)(k0 + k) * ldv + i] * wi;
+        }
     }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -963,6 +982,24 @@ __global__ void __launch_bounds__(kThreads) k_axpy_norm(size_t n, int j, int res
     __syncthreads();
     double acc = 0.0;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
+    if (KC > 0 && vec2_ok(n, n, V, w)) {
+        const size_t n2 = n / 2;
+        double2* w2 = reinterpret_cast<double2*>(w);
+        const double2* __restrict__ V2 = reinterpret_cast<const double2*>(V);
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+            double2 wi = w2[i];
+            double2 vk[KC > 0 ? KC : 1];
+#pragma unroll
+            for (int k = 0; k < KC; ++k) vk[k] = V2[(size_t)k * n2 + i];
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                wi.x -= h[k] * vk[k].x;
+                wi.y -= h[k] * vk[k].y;
+            }
+            w2[i] = wi;
+            acc += wi.x * wi.x + wi.y * wi.y;
+        }
+    } else
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         double wi = w[i];
         if (KC > 0) {
@@ -998,6 +1035,15 @@ __global__ void __launch_bounds__(kThreads) k_scale_next(size_t n, int j, int re
     const double nn = nn_s;
     double* vn = V + (size_t)(j + 1) * n;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
+    if (vec2_ok(n, n, V, w)) {
+        double2* vn2 = reinterpret_cast<double2*>(vn);
+        const double2* __restrict__ w2 = reinterpret_cast<const double2*>(w);
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n / 2; i += stride) {
+            const double2 a = w2[i];
+            vn2[i] = make_double2(a.x / nn, a.y / nn);
+        }
+        return;
+    }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) vn[i] = w[i] / nn;
 }
 
@@ -1028,6 +1074,22 @@ __global__ void __launch_bounds__(kThreads) k_update(size_t n, int restart, cons
     if (threadIdx.x < restart) y[threadIdx.x] = s->y[threadIdx.x];
     __syncthreads();
     const size_t stride = (size_t)gridDim.x * blockDim.x;
+    if (vec2_ok(n, n, Z, x)) {
+        double2* x2 = reinterpret_cast<double2*>(x);
+        const double2* __restrict__ Z2 = reinterpret_cast<const double2*>(Z);
+        const size_t n2 = n / 2;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+            double2 xi = x2[i];
+#pragma unroll 5
+            for (int k = 0; k < restart; ++k) {
+                const double2 z = Z2[(size_t)k * n2 + i];
+                xi.x += y[k] * z.x;
+                xi.y += y[k] * z.y;
+            }
+            x2[i] = xi;
+        }
+        return;
+    }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         double xi = x[i];
         for (int k = 0; k < restart; ++k) xi += y[k] * Z[(size_t)k * n + i];
