@@ -1958,26 +1958,41 @@ static size_t chain_smem_bytes(int nw, int ch) {
            (size_t)(2 * kChainStages + 4) * 8;
 }
 
-// y_k = M_kk t_k for every block at once (grid z = block): the block-diagonal products that frame the chain
-__global__ void __launch_bounds__(256) k_blk_mv_all(int n, const double* __restrict__ Linv, int nblk, const double* t,
-                                                    double* y, int upper, const int* done) {
+// y_k = M_kk t_k for every block at once: the block-diagonal products that frame the chain.  One CTA per (block,
+// instance), thread r owns row r and walks the columns; it reads the TRANSPOSED copy MT of the triangular block
+// (MT[c][r] = M[r][c]), so that every step is one coalesced row segment and only the triangle is read.
+//   upper = 0: M lower triangular (pass MT = transposed inverse blocks);  upper = 1: M upper triangular (pass the
+//   untransposed inverse blocks).
+__global__ void __launch_bounds__(kSolveBlk) k_blk_mv_all(int n, const double* __restrict__ MT, int nblk, const double* t,
+                                                          double* y, int upper, const int* done) {
     if (done && *done) return;
     __shared__ double ts[kSolveBlk];
-    const int ib = blockIdx.y, kb = blockIdx.z;
+    const int kb = blockIdx.x, ib = blockIdx.y;
     const int k0 = kb * kSolveBlk;
     const int w = k0 + kSolveBlk < n ? kSolveBlk : n - k0;
-    for (int i = threadIdx.x; i < w; i += blockDim.x) ts[i] = t[(size_t)ib * n + k0 + i];
+    const int r = threadIdx.x;
+    ts[r] = r < w ? t[(size_t)ib * n + k0 + r] : 0.0;
     __syncthreads();
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= w) return;
-    const int lane = threadIdx.x & 31;
-    const double* Ir = Linv + ((size_t)ib * nblk + kb) * kSolveBlk * kSolveBlk + (size_t)row * kSolveBlk;
-    double a = 0.0;
-    const int c0 = upper ? (row & ~31) : 0, c1 = upper ? w : row + 1;
-    for (int c = c0 + lane; c < c1; c += 32)
-        if (!upper || c >= row) a += Ir[c] * ts[c];
-    a = warp_sum(a);
-    if (lane == 0) y[(size_t)ib * n + k0 + row] = a;
+    const double* Mb = MT + ((size_t)ib * nblk + kb) * kSolveBlk * kSolveBlk + r;
+    double a0 = 0.0, a1 = 0.0;
+    if (!upper) {
+        // warp-uniform bound: the last row of this warp; entries above the diagonal are stored zeros
+        const int cmax = (r | 31) < w ? (r | 31) : w - 1;
+        int c = 0;
+        for (; c + 1 <= cmax; c += 2) {
+            a0 = fma(Mb[(size_t)c * kSolveBlk], ts[c], a0);
+            a1 = fma(Mb[(size_t)(c + 1) * kSolveBlk], ts[c + 1], a1);
+        }
+        if (c <= cmax) a0 = fma(Mb[(size_t)c * kSolveBlk], ts[c], a0);
+    } else {
+        int c = r & ~31;
+        for (; c + 1 < w; c += 2) {
+            a0 = fma(Mb[(size_t)c * kSolveBlk], ts[c], a0);
+            a1 = fma(Mb[(size_t)(c + 1) * kSolveBlk], ts[c + 1], a1);
+        }
+        if (c < w) a0 = fma(Mb[(size_t)c * kSolveBlk], ts[c], a0);
+    }
+    if (r < w) y[(size_t)ib * n + k0 + r] = a0 + a1;
 }
 
 static void launch_chain(cudaStream_t s, int dir, int B, int n, const ChainLayout& cl, const double* W, const double* vin,
@@ -2025,14 +2040,14 @@ void be_chol_solve(stream_t st, const LevelDev& L, int B, const double* Lf, cons
         // L^-1 = Wt^-1 D^-1, L^-T = D^-T Wt^-T: block-diagonal product, two chains, block-diagonal product
         double *Wc, *WTc;
         chain_arrays(cl, B, n, const_cast<double*>(Linv), &Wc, &WTc);
-        k_blk_mv_all<<<dim3(kSolveBlk / 8, B, nblk), 256, 0, s>>>(n, Linv, nblk, rb, y, 0, done);
+        k_blk_mv_all<<<dim3(nblk, B), kSolveBlk, 0, s>>>(n, LinvT, nblk, rb, y, 0, done);
         launch_chain(s, 0, B, n, cl, Wc, y, rb, done);
         if (getenv("PDEOP_CHAIN_DEBUG")) {   // debugging aid: return L^-1 rhs
             k_from_band<<<dim3(cdiv(L.G, kThreads), B), kThreads, 0, s>>>(L, rb, out, done);
             return;
         }
         launch_chain(s, 1, B, n, cl, WTc, rb, y, done);
-        k_blk_mv_all<<<dim3(kSolveBlk / 8, B, nblk), 256, 0, s>>>(n, LinvT, nblk, y, rb, 1, done);
+        k_blk_mv_all<<<dim3(nblk, B), kSolveBlk, 0, s>>>(n, Linv, nblk, y, rb, 1, done);
         k_from_band<<<dim3(cdiv(L.G, kThreads), B), kThreads, 0, s>>>(L, rb, out, done);
         PDEOP_COUNT(3);
         PDEOP_LAUNCH_CHECK();
