@@ -20,6 +20,9 @@
 
 namespace cg = cooperative_groups;
 
+#ifndef PDEOP_APPLY_MINB
+#define PDEOP_APPLY_MINB 2
+#endif
 // load policy of the Gauss-Seidel iterate.  An L2 evict-last hint on these loads (createpolicy + ld.L2::cache_hint)
 // was measured and changes nothing once the streamed operands carry evict-first (ld_stream).
 #ifndef PDEOP_GS_LD
@@ -167,7 +170,7 @@ void be_atb(stream_t st, const LevelDev& L, int B, const double* coef, const dou
 
 // (3 CTAs per SM -- __launch_bounds__(kThreads, 3), 80 registers -- spills 400 bytes per thread: not used)
 template <int D>
-__global__ void __launch_bounds__(kThreads) k_apply(LevelDev L, const double* __restrict__ T,
+__global__ void __launch_bounds__(kThreads, PDEOP_APPLY_MINB) k_apply(LevelDev L, const double* __restrict__ T,
                                                     const double* __restrict__ coef, const double* __restrict__ x,
                                                     const double* __restrict__ b, double* __restrict__ y, int mode,
                                                     const int* done) {

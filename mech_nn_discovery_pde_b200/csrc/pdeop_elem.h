@@ -48,6 +48,13 @@ PDEOP_HD double ld_stream(const double* p) {
 #endif
 #endif
 
+// A/B switch (tools/apply_micro.py): one gather axis in flight in K apply (86 registers; 80 and 3 CTAs/SM with
+// -DPDEOP_APPLY_MINB=3) instead of two (98 registers).  Measured: 345 vs 360 us per fine-level launch -- occupancy
+// is not what limits the kernel; default unchanged.
+#ifndef PDEOP_APPLY_OVERLAP
+#define PDEOP_APPLY_OVERLAP true
+#endif
+
 namespace pdeop {
 
 // 5-point stencil offsets of the central-difference row at line position i (lp_pde_central_diff.py:1000-1006):
@@ -286,7 +293,7 @@ PDEOP_HD void gather_axis_fma(const LevelDev& L, const double* __restrict__ T, i
 // this body are bound by dependent memory round trips, not by bandwidth.
 // BSUB: also loads b (issued with the last axis batch, when the registers of the first axes are free again) and
 // returns acc[m] = b[m] - sum instead of the sum.
-template <int D, class LD, int PITCH, bool SPLIT, bool BSUB>
+template <int D, class LD, int PITCH, bool SPLIT, bool BSUB, bool OVERLAP = true>
 PDEOP_HD void k_gather(const LevelDev& L, const int* __restrict__ rowbase, const double* __restrict__ T,
                        const double* x, const double* __restrict__ b, unsigned w, int i0, int i1, int i2,
                        double acc[1 + 2 * D]) {
@@ -297,10 +304,14 @@ PDEOP_HD void k_gather(const LevelDev& L, const int* __restrict__ rowbase, const
     for (int m = 0; m < M; ++m) acc[m] = 0.0;
     AxisNb nb[D];
     double bl[M];
-    gather_axis_load<D, LD, SPLIT>(L, rb, x, 0, idx[3 - D], i1, nb[0]);
+    if (OVERLAP) gather_axis_load<D, LD, SPLIT>(L, rb, x, 0, idx[3 - D], i1, nb[0]);
 #pragma unroll
     for (int a = 0; a < D; ++a) {
-        if (a + 1 < D) gather_axis_load<D, LD, SPLIT>(L, rb, x, a + 1, idx[3 - D + a + 1], i1, nb[a + 1]);
+        if (OVERLAP) {
+            if (a + 1 < D) gather_axis_load<D, LD, SPLIT>(L, rb, x, a + 1, idx[3 - D + a + 1], i1, nb[a + 1]);
+        } else {   // one axis in flight: fewer registers, more resident warps (streaming kernels without barriers)
+            gather_axis_load<D, LD, SPLIT>(L, rb, x, a, idx[3 - D + a], i1, nb[a]);
+        }
         if (BSUB && a == D - 1) {
 #pragma unroll
             for (int m = 0; m < M; ++m) bl[m] = ld_stream(b + ((unsigned)m * (unsigned)L.G + w));
@@ -423,7 +434,7 @@ PDEOP_HD void apply_k_elem(const LevelDev& L, const double* __restrict__ T, cons
     unpack_coord(L.coord[w], i0, i1, i2);
     const int flags = L.flags[w];
     double acc[M];
-    k_gather<D, LdPlain, kTabPitch, false, false>(L, L.rowbase, T, x, nullptr, 0u, i0, i1, i2, acc);
+    k_gather<D, LdPlain, kTabPitch, false, false, PDEOP_APPLY_OVERLAP>(L, L.rowbase, T, x, nullptr, 0u, i0, i1, i2, acc);
     PointLocal<D> pl;
     load_local<D>(L, T, coef, w, i0, i1, i2, flags, pl);
     double xl[M];
