@@ -2046,10 +2046,6 @@ void be_chol_solve(stream_t st, const LevelDev& L, int B, const double* Lf, cons
         chain_arrays(cl, B, n, const_cast<double*>(Linv), &Wc, &WTc);
         k_blk_mv_all<<<dim3(nblk, B), kSolveBlk, 0, s>>>(n, LinvT, nblk, rb, y, 0, done);
         launch_chain(s, 0, B, n, cl, Wc, y, rb, done);
-        if (getenv("PDEOP_CHAIN_DEBUG")) {   // debugging aid: return L^-1 rhs
-            k_from_band<<<dim3(cdiv(L.G, kThreads), B), kThreads, 0, s>>>(L, rb, out, done);
-            return;
-        }
         launch_chain(s, 1, B, n, cl, WTc, rb, y, done);
         k_blk_mv_all<<<dim3(nblk, B), kSolveBlk, 0, s>>>(n, Linv, nblk, y, rb, 1, done);
         k_from_band<<<dim3(cdiv(L.G, kThreads), B), kThreads, 0, s>>>(L, rb, out, done);
@@ -2070,10 +2066,6 @@ void be_chol_solve(stream_t st, const LevelDev& L, int B, const double* Lf, cons
         }
         k_blk_mv<<<dim3(cdiv(w, 8), B), 256, 0, s>>>(n, Linv, nblk, kb, w, rb, y, 0, done);
         PDEOP_COUNT(1);
-    }
-    if (getenv("PDEOP_CHAIN_DEBUG")) {   // debugging aid: return L^-1 rhs
-        k_from_band<<<dim3(cdiv(L.G, kThreads), B), kThreads, 0, s>>>(L, y, out, done);
-        return;
     }
     // backward: y <- L^-T y.  Per block row (descending): z_k = Linv_kk^T y_k (into rb), then the update kernel
     // stores z_k into y and subtracts L[k rows, c]^T z_k from the band columns left of the block
