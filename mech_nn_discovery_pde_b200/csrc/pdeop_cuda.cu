@@ -227,7 +227,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gs_cluster(LevelDev L, const 
     const int csize = SINGLE ? 1 : (int)cluster.num_blocks();
     const int rank = SINGLE ? 0 : (int)cluster.block_rank();
     const int ib = blockIdx.x / csize;
-    const int tid = rank * blockDim.x + threadIdx.x;
+    // Point idx of a step is handled by "thread" tid = idx mod nthreads.  Warps are dealt round-robin over the
+    // cluster's CTAs (warp-sized chunks keep every access coalesced): a step with fewer points than the cluster has
+    // threads -- most steps on the coarser levels -- spreads over all SMs of the cluster instead of filling CTA 0
+    // first, so each SM's load/store pipe sees 1/csize of the step's gathers.
+    const int tid = (((int)threadIdx.x >> 5) * csize + rank) * 32 + ((int)threadIdx.x & 31);
     const int nthreads = csize * blockDim.x;
     const size_t o = (size_t)ib * L.M * L.G;
     const double* Ti = T + (size_t)ib * L.D * kTabEntries * kTabPitch;
@@ -334,7 +338,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_gs_pipe(LevelDev L, const double
     const int csize = SINGLE ? 1 : (int)cluster.num_blocks();
     const int rank = SINGLE ? 0 : (int)cluster.block_rank();
     const int ib = blockIdx.x / csize;
-    const int tid = rank * blockDim.x + threadIdx.x;
+    // Point idx of a step is handled by "thread" tid = idx mod nthreads.  Warps are dealt round-robin over the
+    // cluster's CTAs (warp-sized chunks keep every access coalesced): a step with fewer points than the cluster has
+    // threads -- most steps on the coarser levels -- spreads over all SMs of the cluster instead of filling CTA 0
+    // first, so each SM's load/store pipe sees 1/csize of the step's gathers.
+    const int tid = (((int)threadIdx.x >> 5) * csize + rank) * 32 + ((int)threadIdx.x & 31);
     const int nthreads = csize * blockDim.x;
     const size_t o = (size_t)ib * L.M * L.G;
     const double* Ti = T + (size_t)ib * L.D * kTabEntries * kTabPitch;
