@@ -131,16 +131,22 @@ void be_unpack(stream_t st, const LevelDev& L, int B, const double* wave, double
     PDEOP_LAUNCH_CHECK();
 }
 
+template <int CC>
 __global__ void __launch_bounds__(kThreads) k_interp(LevelDev Li, LevelDev Lo, int C, const double* __restrict__ in,
                                                      double* __restrict__ out, int add, const int* done) {
     if (done && *done) return;
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= Lo.G) return;
-    interp_elem(Li, Lo, C, in + (size_t)blockIdx.y * C * Li.G, out + (size_t)blockIdx.y * C * Lo.G, w, add);
+    interp_elem<CC>(Li, Lo, C, in + (size_t)blockIdx.y * C * Li.G, out + (size_t)blockIdx.y * C * Lo.G, w, add);
 }
 void be_interp(stream_t st, const LevelDev& Li, const LevelDev& Lo, int B, int C, const double* in, double* out,
                int add, const int* done) {
-    k_interp<<<dim3(cdiv(Lo.G, kThreads), B), kThreads, 0, (cudaStream_t)st>>>(Li, Lo, C, in, out, add, done);
+    const dim3 grid(cdiv(Lo.G, kThreads), B);
+    cudaStream_t cs = (cudaStream_t)st;
+    if (C == 7) k_interp<7><<<grid, kThreads, 0, cs>>>(Li, Lo, C, in, out, add, done);
+    else if (C == 5) k_interp<5><<<grid, kThreads, 0, cs>>>(Li, Lo, C, in, out, add, done);
+    else if (C == 3) k_interp<3><<<grid, kThreads, 0, cs>>>(Li, Lo, C, in, out, add, done);
+    else k_interp<0><<<grid, kThreads, 0, cs>>>(Li, Lo, C, in, out, add, done);
     PDEOP_COUNT(1);
     PDEOP_LAUNCH_CHECK();
 }

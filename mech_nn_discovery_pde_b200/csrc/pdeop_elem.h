@@ -595,8 +595,11 @@ PDEOP_HD void interp_axis(int i, int n_in, int n_out, int& lo, int& hi, double& 
     l0 = 1.0 - l1;
 }
 
+// CC > 0: channel count at compile time (the channel loop unrolls: all gathers of a point in flight together)
+template <int CC = 0>
 PDEOP_HD void interp_elem(const LevelDev& Li, const LevelDev& Lo, int C, const double* __restrict__ in,
                           double* __restrict__ out, int wo, int add) {
+    if (CC > 0) C = CC;
     int i0, i1, i2;
     unpack_coord(Lo.coord[wo], i0, i1, i2);
     int l[3], h[3];
@@ -615,7 +618,8 @@ PDEOP_HD void interp_elem(const LevelDev& Li, const LevelDev& Lo, int C, const d
     const int p101 = (z0 && z2) ? wave_pos(Li, h[0], l[1], h[2]) : p000;
     const int p110 = (z0 && z1) ? wave_pos(Li, h[0], h[1], l[2]) : p000;
     const int p111 = (z0 && z1 && z2) ? wave_pos(Li, h[0], h[1], h[2]) : p000;
-    for (int m = 0; m < C; ++m) {
+#pragma unroll
+    for (int m = 0; m < (CC > 0 ? CC : C); ++m) {
         const double* __restrict__ s = in + (size_t)m * Li.G;
         double a0 = w0[2] * s[p000];
         if (z2) a0 += w1[2] * s[p001];
