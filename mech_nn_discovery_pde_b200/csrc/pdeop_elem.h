@@ -433,17 +433,23 @@ PDEOP_HD void apply_k_elem(const LevelDev& L, const double* __restrict__ T, cons
     int i0, i1, i2;
     unpack_coord(L.coord[w], i0, i1, i2);
     const int flags = L.flags[w];
-    double acc[M];
-    k_gather<D, LdPlain, kTabPitch, false, false, PDEOP_APPLY_OVERLAP>(L, L.rowbase, T, x, nullptr, 0u, i0, i1, i2, acc);
+    // own-point operands first: the gather's load fences would otherwise pin them behind it as one more dependent
+    // memory round trip at the end
     PointLocal<D> pl;
-    load_local<D>(L, T, coef, w, i0, i1, i2, flags, pl);
     double xl[M];
-    double cs = 0.0;
 #pragma unroll
     for (int m = 0; m < M; ++m) {
         xl[m] = x[m * G + w];
-        cs += pl.c[m] * xl[m];
+        pl.c[m] = (flags & 1) ? coef[m * G + w] : 0.0;
     }
+    double acc[M];
+    k_gather<D, LdPlain, kTabPitch, false, false, PDEOP_APPLY_OVERLAP>(L, L.rowbase, T, x, nullptr, 0u, i0, i1, i2, acc);
+#pragma unroll
+    for (int m = 0; m < M; ++m) pl.ini[m] = (double)((flags >> (4 + 2 * m)) & 3);
+    load_axis_local<D, kTabPitch>(T, i0, i1, i2, pl);
+    double cs = 0.0;
+#pragma unroll
+    for (int m = 0; m < M; ++m) cs += pl.c[m] * xl[m];
     double yl[M];
 #pragma unroll
     for (int m = 0; m < M; ++m) yl[m] = acc[m] + pl.c[m] * cs + pl.ini[m] * xl[m];
