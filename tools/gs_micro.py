@@ -10,7 +10,14 @@ from oracle.cases import IV_LISTS
 dims = tuple(int(a) for a in sys.argv[1:4]) if len(sys.argv) >= 4 else (32, 64, 64)
 B = int(os.environ.get("B", "32")); reps = int(os.environ.get("REPS", "5"))
 n_grid = int(os.environ.get("NGRID", "4"))
-lib = _lib.get_library()
+flags = os.environ.get('PDEOP_VARIANT_FLAGS', '')
+if flags:   # A/B testing: build and use a variant library with extra nvcc flags
+    from mech_nn_discovery_pde_b200.build import build_debug
+    so = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libpdeop_variant.so')
+    build_debug(so, flags.split())
+    lib = _lib.PdeopLibrary(so)
+else:
+    lib = _lib.get_library()
 G = int(np.prod(dims)); M = 7
 g = torch.Generator().manual_seed(1)
 coeffs = torch.zeros(B, G, M, dtype=torch.float64); coeffs[..., 0] = 0.1 * torch.randn(B, G, generator=g, dtype=torch.float64)
@@ -32,4 +39,4 @@ e0.record()
 for _ in range(reps): call()
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
-print(f"dims {dims} B {B}: stage(GS x5) incl. 2 pack + 1 unpack kernels: {ms:.3f} ms per call")
+print(f"[{flags}] dims {dims} B {B}: stage(GS x5) incl. 2 pack + 1 unpack kernels: {ms:.3f} ms per call")
