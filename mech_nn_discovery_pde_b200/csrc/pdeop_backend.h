@@ -46,6 +46,9 @@ void be_gs(stream_t st, const LevelDev& L, int B, const double* T, const double*
 inline size_t be_gs_stash_doubles(const LevelDev& L) { return 8 * ((size_t)L.G + 4096); }
 // dinv[m][w] = 1 / K[(w,m),(w,m)]: reciprocal diagonal of K, computed once per operator set-up
 void be_dinv(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, double* dinv);
+// zero what the factorisation and the solves will read of the B dense n x n matrices: the lower band (half-bandwidth bw
+// plus the panel/tile slack of the blocked algorithms); nothing else of the array is ever read
+void be_zero_dense(stream_t st, int B, int n, int bw, double* Kd);
 void be_dense(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, double* Kd);
 // ---- dense coarsest level: storage of the factor's inverse diagonal blocks and (chain solver) scaled band ----
 // Linv area (doubles): [inverse diagonal blocks | their transposes | pad | Wc | WTc], see be_cholesky.

@@ -778,6 +778,26 @@ __global__ void __launch_bounds__(kThreads) k_dense(LevelDev L, const double* __
     dense_elem<D>(L, T + (size_t)blockIdx.y * L.D * kTabEntries * kTabPitch, coef + (size_t)blockIdx.y * n,
                   Kd + (size_t)blockIdx.y * n * n, w);
 }
+// Row r of every matrix: columns [r - bwz, r].  The blocked factorisation reads at most bw + kOuter - 1 columns left
+// of the diagonal (a trailing-update tile row against the first column of its panel), the solves at most bw + 158;
+// nothing reads right of the diagonal.  At n = 14336, bw = 1798, B = 32 this writes 7.9 GB instead of 52.6 GB.
+__global__ void __launch_bounds__(256) k_zero_band(int n, int bwz, double* Kd) {
+    const int r = blockIdx.x;
+    double* row = Kd + ((size_t)blockIdx.y * n + r) * n;
+    const int lo = r - bwz > 0 ? r - bwz : 0;
+    for (int c = lo + threadIdx.x; c <= r; c += blockDim.x) row[c] = 0.0;
+}
+void be_zero_dense(stream_t st, int B, int n, int bw, double* Kd) {
+    const int bwz = bw + 384;   // kOuter (256) + a tile of slack
+    if (bwz >= n - 1 || n < 1024) {
+        note(cudaMemsetAsync(Kd, 0, (size_t)B * n * n * sizeof(double), (cudaStream_t)st));
+        return;
+    }
+    k_zero_band<<<dim3(n, B), 256, 0, (cudaStream_t)st>>>(n, bwz, Kd);
+    PDEOP_COUNT(1);
+    PDEOP_LAUNCH_CHECK();
+}
+
 void be_dense(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, double* Kd) {
     dim3 grid(cdiv(L.G, kThreads), B);
     cudaStream_t s = (cudaStream_t)st;

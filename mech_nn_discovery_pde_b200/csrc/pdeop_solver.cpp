@@ -361,7 +361,7 @@ static void setup_operator(pdeop_plan* pl, const double* coeffs, const double* c
         }
         const int lc = pl->n_grid - 1;
         double* Kd = P_Kd(pl, persist);
-        be_zero(st, Kd, (size_t)B * pl->nc * pl->nc * sizeof(double));
+        be_zero_dense(st, B, pl->nc, pl->lev[lc].dev.bw, Kd);
         be_dense(st, pl->lev[lc].dev, B, P_T(pl, persist, lc), P_coef(pl, persist, lc), Kd);
     }
     ProfScope pf(PC_FACTOR, st);

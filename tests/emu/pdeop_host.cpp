@@ -124,6 +124,8 @@ void be_dinv(stream_t, const LevelDev& L, int B, const double* T, const double* 
         }
 }
 
+void be_zero_dense(stream_t, int B, int n, int, double* Kd) { memset(Kd, 0, (size_t)B * n * n * sizeof(double)); }
+
 void be_dense(stream_t, const LevelDev& L, int B, const double* T, const double* coef, double* Kd) {
     const size_t n = vstride(L);
     for (int ib = 0; ib < B; ++ib)
