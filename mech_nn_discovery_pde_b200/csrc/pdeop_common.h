@@ -29,6 +29,8 @@ constexpr int kTabPitch = 1032;
 // more lets the gather of step t+1 (everything but the backward distance-1 neighbours) run during step t, because
 // the farthest forward neighbour (s+1+4) was then finished by the previous sweep in step t-1, not in step t.
 constexpr int kGsLag = 6;
+// The unsplit kernel gathers and finishes a point in the same step: radius + 1 suffices (4 steps fewer per call).
+constexpr int kGsLagUnsplit = 5;
 constexpr int kMaxRestart = 32;
 // Block size of the dense triangular solves (inverse diagonal blocks).  128: the chain solver prefetches, per CTA,
 // the previous block's columns of its rows (kSolveBlk/4 rows x kSolveBlk columns) into shared memory; at 128 that

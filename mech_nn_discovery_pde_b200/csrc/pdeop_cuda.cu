@@ -264,16 +264,16 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gs_cluster(LevelDev L, const 
         rbuse = rbs + 4;
         hs = hss;
     }
-    const int steps = L.S + kGsLag * (nsweeps - 1);
+    const int steps = L.S + kGsLagUnsplit * (nsweeps - 1);
     // points of step t: the hyperplanes s_k = t - lag*k of the sweeps k in flight, concatenated
     auto step_sweeps = [&](int t, int& k_lo, int& k_hi) -> int {
-        k_lo = (t - (L.S - 1) + kGsLag - 1) / kGsLag;
+        k_lo = (t - (L.S - 1) + kGsLagUnsplit - 1) / kGsLagUnsplit;
         if (k_lo < 0) k_lo = 0;
-        k_hi = t / kGsLag;
+        k_hi = t / kGsLagUnsplit;
         if (k_hi > nsweeps - 1) k_hi = nsweeps - 1;
         int total = 0;
         for (int k = k_lo; k <= k_hi; ++k) {
-            const int s = t - kGsLag * k;
+            const int s = t - kGsLagUnsplit * k;
             total += hs[s + 1] - hs[s];
         }
         return total;
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gs_cluster(LevelDev L, const 
     auto point_of = [&](int t, int k_lo, int k_hi, int idx) -> int {
         int rem = idx;
         for (int k = k_lo; k <= k_hi; ++k) {
-            const int s = t - kGsLag * k;
+            const int s = t - kGsLagUnsplit * k;
             const int h0 = hs[s], cnt = hs[s + 1] - h0;
             if (rem < cnt) return h0 + rem;
             rem -= cnt;
