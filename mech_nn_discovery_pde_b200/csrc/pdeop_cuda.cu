@@ -1217,6 +1217,10 @@ __global__ void __launch_bounds__(128) k_chol_trsm(int n, double* A, size_t stri
         l[i][j] = Ab[(size_t)(k0 + i) * n + k0 + j];
     }
     __syncthreads();
+    // reciprocal diagonal once per CTA: 32 fp64 divisions per row (~40 instructions each) become multiplications
+    __shared__ double rinv[kInner];
+    if (threadIdx.x < nb) rinv[threadIdx.x] = 1.0 / l[threadIdx.x][threadIdx.x];
+    __syncthreads();
     const int r = k0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= r1) return;
     double* row = Ab + (size_t)r * n + k0;
@@ -1229,7 +1233,7 @@ __global__ void __launch_bounds__(128) k_chol_trsm(int n, double* A, size_t stri
             double s = v[j];
 #pragma unroll
             for (int t = 0; t < j; ++t) s -= v[t] * l[j][t];
-            v[j] = s / l[j][j];
+            v[j] = s * rinv[j];
         }
     }
 #pragma unroll
