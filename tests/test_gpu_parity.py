@@ -317,12 +317,14 @@ def test_gs_kernel_variants_bit_identical(lib):
         assert np.array_equal(outs[0], step_kernel)
 
 
-def test_chain_solver_matches_block_row_solver(lib):
+@pytest.mark.parametrize("dims", [(8, 16, 16), (8, 18, 20)])
+def test_chain_solver_matches_block_row_solver(lib, dims):
     """Coarsest-level triangular solves: the persistent chain kernels (block-scaled band, TMA + mbarrier pipeline,
     DSMEM exchange) against the one-launch-per-block-row path, on the same factor, and the residual of the solve.
-    8x8x8 coarsest grid: n = 3584 = 28 block rows, half-bandwidth 1798 (the band structure of the BASELINE grid)."""
+    8x8x8 coarsest grid: n = 3584 = 28 block rows, half-bandwidth 1798 (the band structure of the BASELINE grid);
+    8x9x10: n = 5040 = 39 block rows + a partial one of 48, half-bandwidth 2022."""
     iv = IV_LISTS["gl"]
-    dims, B, n_grid = (8, 16, 16), 3, 2
+    B, n_grid = 3, 2
     G, M = int(np.prod(dims)), 7
     rng = np.random.default_rng(23)
     coeffs = np.zeros((B, G, M))
