@@ -6,8 +6,10 @@
 //   * Krylov vector kernels with fused multi-dot / multi-axpy / norm steps: warp-shuffle + block
 //     reductions, block partials re-summed in a fixed order by the consumer kernel (deterministic,
 //     no host synchronisation; the convergence flag lives in device memory)
-//   * batched dense Cholesky (blocked right-looking, two-level) and blocked triangular solves for the
-//     coarsest multigrid level and the dense layer
+//   * batched dense band Cholesky for the coarsest multigrid level and the dense layer (outer panels of 256
+//     columns, left-looking inside a panel, trailing updates on fp64 DMMA), and its triangular solves: the chain
+//     solver (one persistent cluster kernel per direction: TMA bulk copies, mbarrier stages, st.async exchange
+//     through distributed shared memory) or, for odd / small n, one launch per block row
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -1702,15 +1704,6 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t a, uint32_t parity) {
         if (ok) return;
         if (spin > (1LL << 22)) __trap();
     }
-}
-// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t a, uint32_t rank) {
-    asm volatile(
-        "{\n\t.reg .b32 ra;\n\t"
-        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(a),
-        "r"(rank)
-        : "memory");
 }
 // asynchronous 8-byte store into CTA `rank`'s shared memory (same offset as the local address) that completes
 // 8 transaction bytes on that CTA's mbarrier: data and "it has arrived" travel together, no release fence
