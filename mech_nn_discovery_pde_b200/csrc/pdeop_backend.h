@@ -70,6 +70,9 @@ inline ChainLayout be_chain_layout(int n, int bw) {
     c.use = (n % 2 == 0) && c.nblk >= 8 && c.nbmax + 1 <= 32;   // vector window of nbmax+1 blocks must fit shared memory
     return c;
 }
+// true when be_cholesky / be_chol_solve will use the chain solver for (n, bw): the dense n x n array is then only
+// needed during operator set-up (the solves read the compact scaled band in the Linv area)
+bool be_chain_active(int n, int bw);
 inline size_t be_chol_linv_doubles(int B, int n, int bw) {
     const ChainLayout c = be_chain_layout(n, bw);
     size_t tot = 2 * (size_t)B * c.nblk * kSolveBlk * kSolveBlk;

@@ -1454,6 +1454,8 @@ static bool chain_enabled() {
     return g_chain != 0;
 }
 
+bool be_chain_active(int n, int bw) { return be_chain_layout(n, bw).use && chain_enabled(); }
+
 int be_set_tuning(int key, int value) {
     if (key == 0) {
         gs_tuning();

@@ -81,6 +81,9 @@ struct pdeop_plan {
     size_t off_Kd = 0;  // persist offset of the coarsest dense matrix / factor
     size_t off_Linv = 0;  // persist offset of the inverse diagonal blocks of the factor
     int nc = 0;         // coarsest unknowns per instance
+    // The dense nc x nc array lives in the (per-layer, reused) scratch buffer instead of the (per-forward-call)
+    // persist buffer when the chain solver is active: it is then dead after operator set-up.
+    bool kd_in_scratch = false;
 };
 
 template <class T>
@@ -238,7 +241,8 @@ extern "C" int pdeop_plan_create(int d, const int* dims, int order, int batch, i
     const LevelDev& Lc = pl->lev[n_grid - 1].dev;
     pl->nc = Lc.M * Lc.G;
     pl->off_Kd = poff;
-    poff += (size_t)batch * pl->nc * pl->nc;
+    pl->kd_in_scratch = be_chain_active(pl->nc, Lc.bw);
+    if (!pl->kd_in_scratch) poff += (size_t)batch * pl->nc * pl->nc;
     pl->off_Linv = poff;
     poff += be_chol_linv_doubles(batch, pl->nc, Lc.bw);   // inverse diagonal blocks (+ transposes, + scaled band)
     pl->persist_doubles = poff;
@@ -256,7 +260,7 @@ extern "C" void pdeop_plan_destroy(pdeop_plan* pl) {
 // scratch layout (doubles): [state | atb | x | w | V[restart] | Z[restart] | per level>=1: x,b,r | cwork]
 struct Scratch {
     FgmresState* state;
-    double *atb, *x, *w, *V, *Z, *cwork, *gs_stash;
+    double *atb, *x, *w, *V, *Z, *cwork, *gs_stash, *Kd;
     size_t gs_stash_stride;
     std::vector<double*> lx, lb, lr;
     size_t n0;
@@ -268,6 +272,7 @@ static size_t scratch_doubles(const pdeop_plan* pl, int restart) {
     const LevelDev& L0 = pl->lev[0].dev;
     size_t n0 = (size_t)pl->B * L0.M * L0.G;
     size_t tot = state_doubles() + n0 * (3 + 2 * (size_t)std::max(restart, 1));
+    if (pl->kd_in_scratch) tot += (size_t)pl->B * pl->nc * pl->nc;
     for (int l = 1; l < pl->n_grid; ++l) tot += 3 * (size_t)pl->B * pl->lev[l].dev.M * pl->lev[l].dev.G;
     tot += 2 * (size_t)pl->B * pl->nc;
     tot += (size_t)pl->B * be_gs_stash_doubles(L0);
@@ -279,6 +284,11 @@ static Scratch carve(const pdeop_plan* pl, void* scratch, int restart) {
     double* p = (double*)scratch;
     s.state = (FgmresState*)p;
     p += state_doubles();
+    s.Kd = nullptr;
+    if (pl->kd_in_scratch) {   // first, so that its place does not depend on `restart`
+        s.Kd = p;
+        p += (size_t)pl->B * pl->nc * pl->nc;
+    }
     const LevelDev& L0 = pl->lev[0].dev;
     s.n0 = (size_t)pl->B * L0.M * L0.G;
     s.atb = p; p += s.n0;
@@ -338,7 +348,9 @@ static int check_backend() {
 static double* P_T(const pdeop_plan* pl, void* persist, int l) { return (double*)persist + pl->lev[l].off_T; }
 static double* P_coef(const pdeop_plan* pl, void* persist, int l) { return (double*)persist + pl->lev[l].off_coef; }
 static double* P_dinv(const pdeop_plan* pl, void* persist, int l) { return (double*)persist + pl->lev[l].off_dinv; }
-static double* P_Kd(const pdeop_plan* pl, void* persist) { return (double*)persist + pl->off_Kd; }
+static double* P_Kd(const pdeop_plan* pl, void* persist, const Scratch& sc) {
+    return pl->kd_in_scratch ? sc.Kd : (double*)persist + pl->off_Kd;
+}
 static double* P_Linv(const pdeop_plan* pl, void* persist) { return (double*)persist + pl->off_Linv; }
 
 // Operator set-up: level-0 coefficients into wave layout, coarse coefficients by linear interpolation
@@ -360,12 +372,12 @@ static void setup_operator(pdeop_plan* pl, const double* coeffs, const double* c
             be_dinv(st, L, B, P_T(pl, persist, l), P_coef(pl, persist, l), P_dinv(pl, persist, l));
         }
         const int lc = pl->n_grid - 1;
-        double* Kd = P_Kd(pl, persist);
+        double* Kd = P_Kd(pl, persist, sc);
         be_zero_dense(st, B, pl->nc, pl->lev[lc].dev.bw, Kd);
         be_dense(st, pl->lev[lc].dev, B, P_T(pl, persist, lc), P_coef(pl, persist, lc), Kd);
     }
     ProfScope pf(PC_FACTOR, st);
-    be_cholesky(st, B, pl->nc, pl->lev[pl->n_grid - 1].dev.bw, P_Kd(pl, persist), P_Linv(pl, persist), sc.state);
+    be_cholesky(st, B, pl->nc, pl->lev[pl->n_grid - 1].dev.bw, P_Kd(pl, persist, sc), P_Linv(pl, persist), sc.state);
 }
 
 static void vcycle(pdeop_plan* pl, const pdeop_solver_cfg* cfg, void* persist, Scratch& sc, int l, const double* b,
@@ -390,7 +402,7 @@ static void vcycle(pdeop_plan* pl, const pdeop_solver_cfg* cfg, void* persist, S
     }
     if (l + 1 == pl->n_grid - 1) {
         ProfScope ps(PC_COARSE_SOLVE, st);
-        be_chol_solve(st, Lc, B, P_Kd(pl, persist), P_Linv(pl, persist), sc.lb[l + 1], sc.lx[l + 1], sc.cwork, done);
+        be_chol_solve(st, Lc, B, P_Kd(pl, persist, sc), P_Linv(pl, persist), sc.lb[l + 1], sc.lx[l + 1], sc.cwork, done);
     } else {
         be_zero(st, sc.lx[l + 1], (size_t)B * Lc.M * Lc.G * sizeof(double));
         vcycle(pl, cfg, persist, sc, l + 1, sc.lb[l + 1], sc.lx[l + 1], sc.lr[l + 1], st);
@@ -528,7 +540,7 @@ extern "C" int pdeop_dense_forward(pdeop_plan* pl, const double* coeffs, const d
     const double* bvp[1] = {bv0};
     setup_operator(pl, coeffs, cvp, fvp, bvp, persist, sc, stream);
     be_atb(stream, pl->lev[0].dev, pl->B, P_coef(pl, persist, 0), rhs, iv_rhs, sc.atb);
-    be_chol_solve(stream, pl->lev[0].dev, pl->B, P_Kd(pl, persist), P_Linv(pl, persist), sc.atb, sc.x, sc.cwork, nullptr);
+    be_chol_solve(stream, pl->lev[0].dev, pl->B, P_Kd(pl, persist, sc), P_Linv(pl, persist), sc.atb, sc.x, sc.cwork, nullptr);
     be_unpack(stream, pl->lev[0].dev, pl->B, sc.x, x_out);
     if (info_out) be_fg_info(stream, sc.state, info_out);
     return check_backend();
@@ -543,7 +555,7 @@ extern "C" int pdeop_dense_backward(pdeop_plan* pl, const double* rhs, const dou
     Scratch sc = carve(pl, scratch, 1);
     be_state_reset(stream, sc.state);
     be_pack(stream, pl->lev[0].dev, pl->B, grad_x, sc.atb);
-    be_chol_solve(stream, pl->lev[0].dev, pl->B, P_Kd(pl, persist), P_Linv(pl, persist), sc.atb, sc.x, sc.cwork, nullptr);  // dz (:65)
+    be_chol_solve(stream, pl->lev[0].dev, pl->B, P_Kd(pl, persist, sc), P_Linv(pl, persist), sc.atb, sc.x, sc.cwork, nullptr);  // dz (:65)
     if (info_out) be_fg_info(stream, sc.state, info_out);
     run_grads(pl, persist, sc, rhs, cv0, fv0, bv0, x, sc.x, d_coeffs, d_rhs, d_iv_rhs, d_cv, d_fv, d_bv, stream);
     return check_backend();
@@ -617,7 +629,7 @@ extern "C" int pdeop_stage(pdeop_plan* pl, const pdeop_solver_cfg* cfg, int stag
         case PDEOP_STAGE_COARSE_SOLVE:
             if (level != pl->n_grid - 1) return fail("coarse solve runs on the last level");
             be_pack(stream, L, B, in1, t1);
-            be_chol_solve(stream, L, B, P_Kd(pl, persist), P_Linv(pl, persist), t1, t2, sc.cwork, nullptr);
+            be_chol_solve(stream, L, B, P_Kd(pl, persist, sc), P_Linv(pl, persist), t1, t2, sc.cwork, nullptr);
             be_unpack(stream, L, B, t2, out);
             break;
         case PDEOP_STAGE_ATB:

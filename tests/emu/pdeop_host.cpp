@@ -32,6 +32,7 @@ void be_event_record(void*, stream_t) {}
 float be_event_elapsed_ms(void*, void*) { return 0.f; }
 long long be_launch_count() { return 0; }
 int be_set_tuning(int, int) { return 0; }
+bool be_chain_active(int, int) { return false; }
 
 static inline size_t vstride(const LevelDev& L) { return (size_t)L.M * L.G; }
 static inline size_t tstride(const LevelDev& L) { return (size_t)L.D * kTabEntries * kTabPitch; }
