@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Benchmark of the differentiable PDE-layer solve (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload gl32|gl_ref|burgers|gl64]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload gl32|gl32_dsf|gl_ref|burgers|gl64|kamani|sine]
 
 A "step" is one forward+backward of the multigrid PDE layer over one batch of synthetic instances
 (SURVEY.md section 8(d) inputs).  Default workload: Ginzburg-Landau 32x64x64 space-time grid, 32 instances
@@ -9,8 +10,15 @@ per GPU, n_grid=4, downsample_first=False (as in the reference's GL script), fp6
 is sharded (weak scaling: 32 instances per GPU) with no communication inside the solve; the only
 collective is the all-reduce of the learned-parameter gradient.
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the reference algorithm on the host CPU
-(the oracle port: the Python reference itself cannot travel to the GPU box) on a bounded sample.
+The other BASELINE.json configurations are selectable with --workload: `kamani` (dense layer, (24,) grid, batch
+4096), `sine` (dense layer, 32x32, batch 1), `burgers` (256x256, batch 64), `gl64` (64x128x128, 32 per GPU: the
+grid of the scaling configuration).
+
+Prints ONE JSON line (rank 0).  `value` is timed with the library's instrumentation OFF; the per-kernel-group
+breakdown and the roofline come from a second, separately timed pass with per-plan instrumentation on.
+`--impl reference` times the reference's algorithm on the host CPU on a bounded sample: the oracle port for the
+workload itself and, when oracle/_ref (the unmodified reference + stub modules, built by oracle/make_ref.py) is
+present, the unmodified reference on its own default Ginzburg-Landau configuration as a cross-check.
 """
 import argparse
 import json
@@ -41,6 +49,11 @@ WORKLOADS = {
                    desc="Ginzburg-Landau reference default 8x32x32, batch 32/GPU, n_grid=3, downsample_first=False"),
     "burgers": dict(dims=(256, 256), iv="burgers", batch=64, n_grid=6, dsf=True, h=(0.025, 20.0 / 256),
                     desc="Burgers 256x256, batch 64/GPU, n_grid=6, downsample_first=True"),
+    # dense layer (PDEDenseLayer): discovery/kamani.py:45-46,153-165 and fit/sine_pde_dense.py:98,106-119
+    "kamani": dict(dims=(24,), iv="kamani", batch=4096, n_grid=1, dsf=True, h=(0.0314,), dense=True,
+                   desc="Kamani ODE (24,) dense layer, batch 4096/GPU"),
+    "sine": dict(dims=(32, 32), iv="sine", batch=1, n_grid=1, dsf=True, h=(0.05, 0.05), dense=True,
+                 desc="sine fit 32x32 dense layer, batch 1"),
 }
 
 IV_LISTS = {
@@ -58,6 +71,17 @@ IV_LISTS = {
         lambda nx, ny: (1, 0, [1, 0], [nx - 1, 0]),
         lambda nx, ny: (1, 0, [0, ny - 1], [nx - 1, ny - 1]),
     ],
+    # discovery/kamani.py:153-156
+    "kamani": [
+        lambda nt: (0, 0, [0], [0]),
+    ],
+    # fit/sine_pde_dense.py:111-115
+    "sine": [
+        lambda nx, ny: (0, 0, [0, 0], [0, ny - 2]),
+        lambda nx, ny: (1, 0, [1, 0], [nx - 1, 0]),
+        lambda nx, ny: (0, 0, [nx - 1, 1], [nx - 1, ny - 2]),
+        lambda nx, ny: (1, 0, [0, ny - 1], [nx - 1, ny - 1]),
+    ],
 }
 
 
@@ -72,9 +96,13 @@ def synth_inputs(wl, B, seed):
     field = torch.randn(B, G, generator=g, dtype=torch.float64)
     if wl["iv"] == "gl":
         coeffs[..., 1] = 1.0
-    else:  # burgers: u_t + p u_x - 0.1 u_xx
+    elif wl["iv"] == "burgers":  # u_t + p u_x - 0.1 u_xx
         coeffs[..., 1] = 1.0
         field = torch.rand(B, G, generator=g, dtype=torch.float64)
+    elif wl["iv"] == "kamani":   # c0 = 1 + 0.1 N, c1 = 0.1 + |N|
+        coeffs[..., 1] = 0.1 + torch.randn(B, G, generator=g, dtype=torch.float64).abs()
+    else:                        # sine: coefficients ~ N(0,1), constant over the grid
+        coeffs[:] = torch.randn(B, 1, M, generator=g, dtype=torch.float64)
     rhs = 0.1 * torch.randn(B, G, generator=g, dtype=torch.float64)
     steps = [torch.full((B, n - 1), h, dtype=torch.float64) for n, h in zip(dims, wl["h"])]
     return dict(coeffs_base=coeffs, field=field, rhs=rhs, steps=steps, G=G, M=M, d=d, gen=g)
@@ -88,15 +116,23 @@ def assemble_coeffs(wl, base, field, theta):
         coeffs[..., 0] = theta[0] * field
         coeffs[..., 1 + d + 1] = theta[1]
         coeffs[..., 1 + d + 2] = theta[2]
-    else:
+    elif wl["iv"] == "burgers":
         coeffs[..., 2] = theta[0] * field
         coeffs[..., 4] = theta[1]
+    elif wl["iv"] == "kamani":
+        coeffs[..., 0] = theta[0] + theta[1] * field
+    else:
+        coeffs[..., 0] = coeffs[..., 0] * theta[0]
     return coeffs
 
 
 def theta_init(wl, device):
     if wl["iv"] == "gl":
         return torch.tensor([0.1, -1.0, -1.0], dtype=torch.float64, device=device, requires_grad=True)
+    if wl["iv"] == "kamani":
+        return torch.tensor([1.0, 0.1], dtype=torch.float64, device=device, requires_grad=True)
+    if wl["iv"] == "sine":
+        return torch.tensor([1.0], dtype=torch.float64, device=device, requires_grad=True)
     return torch.tensor([1.0, -0.1], dtype=torch.float64, device=device, requires_grad=True)
 
 
@@ -153,8 +189,8 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def algorithmic_bytes(plan, cfgs, B):
-    """Per-launch algorithmic bytes of the HBM-bound kernel groups."""
+def algorithmic_bytes(plan, wl, cfgs, B):
+    """Per-launch algorithmic bytes / flops of the kernel groups."""
     from mech_nn_discovery_pde_b200 import _lib
     w = 8
     M = plan.M
@@ -169,11 +205,16 @@ def algorithmic_bytes(plan, cfgs, B):
         "gs_fine": 4 * M * w * G0 * B * nsw,               # per sweep: read x, b, coeffs; write x
         "apply_fine": 3 * M * w * G0 * B,                   # read z, coeffs; write y  (residual: +b)
         "coarse_solve": 2 * nc * (bw + 1) * w * B,          # band of L streamed once per triangular solve
+        "factor_flops": B * nc * (bw + 1.0) * (bw + 2.0),   # band Cholesky: n*bw^2 multiply-adds = 2x flops / 2
     }
 
 
+PARAM_GRAD_DOUBLES = 4 * (512 * 1024 + 1024 * 1024 + 1024 * 10)   # the GL model's four ParamNets
+
+
 def run_ours(args, wl):
-    from mech_nn_discovery_pde_b200 import MultigridLayer, PDEConfig, _lib
+    from mech_nn_discovery_pde_b200 import MultigridLayer, PDEConfig, PDEDenseLayer
+    from mech_nn_discovery_pde_b200 import parallel
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -185,16 +226,28 @@ def run_ours(args, wl):
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch or wl["batch"]
     dims = wl["dims"]
-    layer = MultigridLayer(bs=B, coord_dims=dims, order=2, n_ind_dim=1, n_iv=1, n_grid=wl["n_grid"],
-                           downsample_first=wl["dsf"], init_index_mi_list=IV_LISTS[wl["iv"]], n_iv_steps=1)
-    lib = _lib.get_library()
-    plan = layer.mg_solver.plan
+    dense = bool(wl.get("dense"))
+    if dense:
+        layer = PDEDenseLayer(bs=B, coord_dims=dims, order=2, n_ind_dim=1, n_iv=1,
+                              init_index_mi_list=IV_LISTS[wl["iv"]], n_iv_steps=1, device=dev)
+        plan = layer.plan
+    else:
+        layer = MultigridLayer(bs=B, coord_dims=dims, order=2, n_ind_dim=1, n_iv=1, n_grid=wl["n_grid"],
+                               downsample_first=wl["dsf"], init_index_mi_list=IV_LISTS[wl["iv"]], n_iv_steps=1,
+                               device=dev)
+        plan = layer.mg_solver.plan
+    lib = plan.lib
     inp = synth_inputs(wl, B, 1234 + rank)
     n_init = plan.n_init
     iv_host = 0.5 * torch.randn(B, n_init, generator=inp["gen"], dtype=torch.float64)
     host = dict(base=inp["coeffs_base"].pin_memory(), field=inp["field"].pin_memory(), rhs=inp["rhs"].pin_memory(),
                 iv=iv_host.pin_memory(), steps=[s.pin_memory() for s in inp["steps"]])
+    u0_host = torch.empty(B, 1, inp["G"], dtype=torch.float64).pin_memory()
     theta = theta_init(wl, dev)
+    # stand-in for the learned ParamNets of the discovery model: their gradient is what the training step
+    # all-reduces (~50 MB fp64).  theta's gradient is scattered into it so the collective carries live data.
+    pnet = torch.zeros(PARAM_GRAD_DOUBLES, dtype=torch.float64, device=dev, requires_grad=True)
+    pnet.grad = torch.zeros_like(pnet)
 
     def to_dev():
         return dict(base=host["base"].to(dev, non_blocking=True), field=host["field"].to(dev, non_blocking=True),
@@ -208,10 +261,10 @@ def run_ours(args, wl):
         u0, u, _ = layer(coeffs, dv["rhs"], dv["iv"], list(dv["steps"]))
         loss = (u0 * u0).sum()          # upstream gradient g = 2 u0
         loss.backward()
+        pnet.grad[:theta.numel()] = theta.grad
         if world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(theta.grad)   # the only collective: learned-parameter gradient
-        return loss
+            parallel.allreduce_param_grads([theta, pnet])   # the only collective: learned-parameter gradients
+        return loss, u0
 
     resident = to_dev()
     torch.cuda.synchronize()
@@ -225,10 +278,10 @@ def run_ours(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- pass 1: `value`, instrumentation off -------------------------------------------------------------
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    lib.profile_enable(True)
     launches0 = lib.launch_count()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -239,23 +292,34 @@ def run_ours(args, wl):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = lib.launch_count() - launches0
-    prof = lib.profile_collect()
-    lib.profile_enable(False)
     clocks = sampler.stop() if rank == 0 else None
     fwd_info, bwd_info = layer.solver_info()
 
-    # end to end through the public layer with HOST buffers: H2D of the step's inputs and D2H of the loss inside
+    # ---- pass 2: end to end through the public layer with HOST buffers: H2D of the step's inputs, D2H of u0 and
+    # ---- of the loss inside the timed region ---------------------------------------------------------------
     barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(args.steps):
         dv = to_dev()
-        loss = step(dv)
+        loss, u0 = step(dv)
+        u0_host.copy_(u0.detach().reshape(u0_host.shape), non_blocking=True)
         _ = float(loss.item())
     t1.record()
     barrier()
     ms_e2e = t0.elapsed_time(t1)
     h2d = sum(t.numel() * 8 for t in [host["base"], host["field"], host["rhs"], host["iv"]] + host["steps"])
+    d2h = u0_host.numel() * 8 + 8
+
+    # ---- pass 3: per-kernel-group device times (events on the launching stream), separately timed ------------
+    prof_steps = max(1, min(args.steps, 3))
+    plan.profile_enable(True)
+    barrier()
+    for _ in range(prof_steps):
+        step(resident)
+    barrier()
+    prof = plan.profile_collect()
+    plan.profile_enable(False)
 
     tt = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -280,21 +344,24 @@ def run_ours(args, wl):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     cfgs = dict(gs_pre=int(PDEConfig.mg_gauss_seidel_steps_pre))
-    ab = algorithmic_bytes(plan, cfgs, B)
+    ab = algorithmic_bytes(plan, wl, cfgs, B)
     total_prof_ms = sum(v[0] for v in prof.values()) or 1.0
-    breakdown = {k: {"ms_per_step": v[0] / args.steps, "groups_per_step": v[1] / args.steps,
+    breakdown = {k: {"ms_per_step": v[0] / prof_steps, "groups_per_step": v[1] / prof_steps,
                      "share": v[0] / total_prof_ms} for k, v in prof.items() if v[1] > 0}
-    for k in ab:
+    for k in ("gs_fine", "apply_fine", "coarse_solve"):
         if k in breakdown and prof[k][1] > 0:
             avg_s = prof[k][0] / 1e3 / prof[k][1]
             breakdown[k]["algorithmic_gbs"] = ab[k] / avg_s / 1e9
             breakdown[k]["frac_of_hbm_peak"] = ab[k] / avg_s / 1e9 / hbm_peak
+    if "factor" in breakdown:
+        avg_s = prof["factor"][0] / 1e3 / prof["factor"][1]
+        breakdown["factor"]["fp64_tflops"] = ab["factor_flops"] / avg_s / 1e12
     hbm_kernels = [k for k in ("gs_fine", "coarse_solve", "apply_fine") if k in breakdown]
     dom = max(hbm_kernels, key=lambda k: breakdown[k]["ms_per_step"])
     traffic = None
-    try:   # DRAM bytes per launch of this kernel from the committed ncu --set full capture (profiles/)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        if dom in tj and args.workload == "gl32" and B == wl["batch"]:
+    try:   # DRAM bytes per launch of this kernel from the committed ncu --set full capture of this round (profiles/)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        if dom in tj and args.workload == tj.get("workload") and B == wl["batch"]:
             traffic = tj[dom]["bytes"]
     except Exception:
         pass
@@ -310,10 +377,13 @@ def run_ours(args, wl):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["desc"], "batch_per_gpu": B, "global_batch": B * world,
-                   "fgmres": "restart 10, maxiter 40, atol 1e-5, GS 5+5, 1 V-cycle", "parallelism": f"batch-shard x{world}",
-                   "l2": "inputs larger than L2 (every vector >= 235 MB)"},
+                   "solver": ("dense Cholesky" if dense else "fgmres restart 10, maxiter 40, atol 1e-5, GS 5+5, 1 V-cycle"),
+                   "parallelism": f"batch-shard x{world}",
+                   "collective": f"all-reduce of {(PARAM_GRAD_DOUBLES + theta.numel()) * 8 / 1e6:.1f} MB fp64 parameter gradients per step",
+                   "l2": "inputs larger than L2 (every vector >= 235 MB)" if not dense else
+                         "working set per step larger than L2" if B * plan.n * plan.n * 8 > 126e6 else "L2 not flushed (working set < L2)"},
         "fgmres_info": {"forward": fwd_info, "backward": bwd_info},
-        "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+        "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "roofline": roofline, "breakdown": breakdown, "cpu_baseline": cpu, "clocks": clocks,
@@ -325,17 +395,37 @@ def run_ours(args, wl):
 
 
 # -------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference algorithm on the host cores (bounded sample)
+# CPU arm: the reference algorithm on the host cores (bounded sample)
 # -------------------------------------------------------------------------------------------------------------
-def cpu_sample(wl, seconds_budget=60.0, iters=1):
-    """One instance of the workload on the CPU: operator set-up measured once, `iters` Arnoldi steps
-    (V-cycle + normal matvec + Gram-Schmidt) measured and extrapolated to the 40+40 iterations the layer runs."""
+def cpu_sample(wl, seconds_budget=60.0, iters=5):
+    """One instance of the workload on the CPU with the oracle port of the reference algorithm.
+
+    Multigrid workloads: operator set-up measured once; then `iters` Arnoldi steps (V-cycle + normal matvec +
+    Gram-Schmidt) of the FORWARD solve and `iters` of the BACKWARD solve (right-hand side 2 u0 of the partial
+    forward iterate: a real backward, same operator) are measured and extrapolated to the 40 + 40 iterations the
+    layer runs; the gradient formulas are measured too.  Dense workloads: the full layer forward+backward."""
     from oracle import pde_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     dims = wl["dims"]
     iv = IV_LISTS[wl["iv"]]
     t0 = time.time()
     st = O.build_structure(dims, iv)
+    if wl.get("dense"):
+        B = min(wl["batch"], 256)
+        inp = synth_inputs(wl, B, 1234)
+        theta = theta_init(wl, "cpu").detach()
+        coeffs = assemble_coeffs(wl, inp["coeffs_base"], inp["field"], theta).numpy()
+        iv_rhs = 0.5 * np.random.default_rng(0).standard_normal((B, st.n_init))
+        steps = [s.numpy() for s in inp["steps"]]
+        t1 = time.time()
+        res = O.dense_layer(dims, iv, coeffs, inp["rhs"].numpy(), iv_rhs, steps)
+        g = np.zeros((B, st.G, st.M))
+        g[:, :, 0] = 2.0 * res.x.reshape(B, st.G, st.M)[:, :, 0]
+        O.dense_layer(dims, iv, coeffs, inp["rhs"].numpy(), iv_rhs, steps, grad_out=g.reshape(B, -1))
+        dt = time.time() - t1
+        return {"value": B / dt, "unit": "solves/s", "cores": os.cpu_count(), "kind": "port",
+                "sample": f"{B} instance(s) of the workload, full dense forward+backward with the oracle port "
+                          f"({dt:.2f}s; LAPACK Cholesky, all cores)"}
     inp = synth_inputs(wl, 1, 1234)
     theta = theta_init(wl, "cpu").detach()
     coeffs = assemble_coeffs(wl, inp["coeffs_base"], inp["field"], theta).numpy()
@@ -344,47 +434,75 @@ def cpu_sample(wl, seconds_budget=60.0, iters=1):
                     wl["dsf"])
     t_setup = time.time() - t0
     K0 = mg.K_list[0]
-    v = mg.Atb0 / np.linalg.norm(mg.Atb0)
-    V = [v]
-    t_it = []
-    for j in range(iters):
-        t1 = time.time()
-        z = O.v_cycle_start(mg, V[-1])
-        u = K0 @ z
-        Vm = np.stack(V, axis=1)
-        h = Vm.T @ u
-        u = u - Vm @ h
-        V.append(u / np.linalg.norm(u))
-        t_it.append(time.time() - t1)
-        if time.time() - t0 > seconds_budget:
-            break
-    t_iter = float(np.mean(t_it))
-    n_iters = 80
-    total = t_setup + n_iters * t_iter
+
+    def arnoldi(b, back):
+        v = b / np.linalg.norm(b)
+        V, Z, t_it = [v], [], []
+        for j in range(iters):
+            t1 = time.time()
+            z = O.v_cycle_start(mg, V[-1], back=back)
+            u = K0 @ z
+            Vm = np.stack(V, axis=1)
+            h = Vm.T @ u
+            u = u - Vm @ h
+            V.append(u / np.linalg.norm(u))
+            Z.append(z)
+            t_it.append(time.time() - t1)
+            if time.time() - t0 > seconds_budget:
+                break
+        return Z, t_it
+    Zf, tf = arnoldi(mg.Atb0, False)
+    x_part = np.sum(Zf, axis=0)                       # some iterate in the forward Krylov space
+    g = np.zeros((st.G, st.M))
+    g[:, 0] = 2.0 * x_part.reshape(st.G, st.M)[:, 0]
+    Zb, tb = arnoldi(g.reshape(-1), True)
+    t1 = time.time()
+    x2, dz2 = x_part.reshape(1, -1), np.sum(Zb, axis=0).reshape(1, -1)
+    lam = mg.b0 - np.stack([mg.A0[0] @ x2[0]])
+    O._grads(st, mg.A0, x2, lam, dz2, None, None, 1)
+    t_grads = time.time() - t1
+    tfm, tbm = float(np.mean(tf)), float(np.mean(tb))
+    total = t_setup + 40 * tfm + 40 * tbm + t_grads
     return {"value": 1.0 / total, "unit": "solves/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"1 instance of the workload: operator set-up measured once ({t_setup:.1f}s) + {len(t_it)} "
-                      f"Arnoldi step(s) (V-cycle+matvec+CGS, {t_iter:.2f}s each) extrapolated to 40 fwd + 40 bwd "
-                      f"iterations; scipy triangular solves are single-threaded, BLAS uses all cores",
-            "setup_s": t_setup, "arnoldi_step_s": t_iter}
+            "sample": f"1 instance of the workload: operator set-up measured once ({t_setup:.1f}s) + {len(tf)} forward "
+                      f"and {len(tb)} backward Arnoldi steps (V-cycle+matvec+CGS; {tfm:.2f}s / {tbm:.2f}s each) "
+                      f"extrapolated to 40 + 40 iterations + gradients ({t_grads:.2f}s); scipy triangular solves are "
+                      f"single-threaded, BLAS uses all cores",
+            "setup_s": t_setup, "arnoldi_step_fwd_s": tfm, "arnoldi_step_bwd_s": tbm, "measured_s": time.time() - t0}
+
+
+def reference_unmodified_sample():
+    """The UNMODIFIED reference (oracle/_ref: the reference's Python files + the stub modules, see
+    oracle/make_ref.py) on its own default Ginzburg-Landau configuration (8x32x32, n_grid 3, downsample_first
+    False, discovery/ginzburg_landau.py:52-57,241-243), batch 2, forward+backward, in a subprocess."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    runner = os.path.join(ROOT, "oracle", "run_ref.py")
+    if not os.path.isdir(os.path.join(ref_dir, "solver")):
+        return {"unavailable": "oracle/_ref not built (python oracle/make_ref.py needs /root/reference)"}
+    try:
+        out = subprocess.run([sys.executable, runner, "gl_ref", "2"], capture_output=True, text=True, timeout=900)
+        line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+        if out.returncode != 0 or not line:
+            return {"unavailable": "oracle/run_ref.py failed: " + (out.stderr.strip().splitlines() or ["?"])[-1][:200]}
+        return json.loads(line[-1])
+    except Exception as e:   # noqa: BLE001
+        return {"unavailable": f"oracle/run_ref.py: {e}"}
 
 
 def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    res = None
-    vals = []
-    for i in range(max(1, min(args.steps, 3))):
-        res = cpu_sample(wl, seconds_budget=args.cpu_budget, iters=1)
-        vals.append(res["value"])
-    value = float(np.mean(vals))
-    res["value"] = value
+    res = cpu_sample(wl, seconds_budget=args.cpu_budget, iters=5)
+    value = res["value"]
+    unmod = None if args.no_unmodified_reference else reference_unmodified_sample()
     out = {"impl": "reference", "metric": "PDE-layer fwd+bwd solves/sec (GL grid, fp64)", "value": value,
            "unit": "solves/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": wl["desc"], "note": "reference algorithm on host CPU (oracle port), per-instance rate"},
-           "cpu_baseline": res,
+           "config": {"workload": wl["desc"], "note": "reference algorithm on host CPU (oracle port), per-instance rate, "
+                                                        "bounded sample extrapolated to the layer's 40+40 iterations"},
+           "cpu_baseline": res, "reference_unmodified": unmod,
            "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -399,6 +517,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU (default: workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=120.0)
+    ap.add_argument("--no-unmodified-reference", action="store_true",
+                    help="reference arm: skip the unmodified-reference cross-check (oracle/_ref)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -10,6 +10,8 @@
  *  - all data pointers are DEVICE pointers to contiguous fp64 unless stated otherwise;
  *  - `stream` is a cudaStream_t passed as void*; every call is asynchronous and stream-ordered, no
  *    call synchronises the host, allocates device memory or creates streams (plan_create excepted);
+ *  - no mutable process-global state: kernel-variant switches and instrumentation belong to a plan; plans on
+ *    different devices (or driven by different host threads) do not interact;
  *  - the caller owns every buffer (sizes from pdeop_plan_query); the library owns only the immutable
  *    plan (index tables, level dims);
  *  - return value 0 = ok, nonzero = error, text from pdeop_last_error();
@@ -77,6 +79,18 @@ enum pdeop_stage {
  *                  (the iv lambdas of init_index_mi_list evaluated at that level's dims, multigrid.py:296-306) */
 int pdeop_plan_create(int d, const int* dims, int order, int batch, int n_grid, int downsample_first, int n_iv,
                       const int* iv_desc, pdeop_plan** out);
+/* Same with creation-time options (NULL = defaults).  The plan records the CUDA device that is current when it is
+ * created; its tables live there and every later call must be made with that device current (checked). */
+typedef struct pdeop_plan_opts {
+    int evolution;      /* PDESYSLP(evolution=...) equation rows (lp_pde_central_diff.py:756-759); 0 default */
+    int chain;          /* coarsest triangular solves: -1 default (environment PDEOP_CHAIN, else on), 0 one launch per
+                           block row, 1 persistent chain kernels where they apply.  Fixed for the plan's lifetime: the
+                           persist/scratch layout depends on it. */
+    int gs_pipe;        /* -1 default (environment PDEOP_GS_PIPE, else 2); see pdeop_plan_set_tuning key 0 */
+    int reserved[5];    /* must be 0 */
+} pdeop_plan_opts;
+int pdeop_plan_create_ex(int d, const int* dims, int order, int batch, int n_grid, int downsample_first, int n_iv,
+                         const int* iv_desc, const pdeop_plan_opts* opts, pdeop_plan** out);
 void pdeop_plan_destroy(pdeop_plan* plan);
 int pdeop_plan_query(const pdeop_plan* plan, int what, int level, long long* out);
 const char* pdeop_last_error(void);
@@ -125,22 +139,22 @@ int pdeop_stage(pdeop_plan* plan, const pdeop_solver_cfg* cfg, int stage, int le
 int pdeop_fgmres(pdeop_plan* plan, const pdeop_solver_cfg* cfg, int back, const double* b, double* x_out,
                  double* info_out, double* hess_out, void* persist, void* scratch, void* stream);
 
-/* Instrumentation (bench.py): per-category device time measured with events recorded on the launching
- * stream around each kernel group, and the number of kernels this library has launched.
+/* Instrumentation (bench.py), PER PLAN: device time per kernel category measured with events recorded on the
+ * launching stream around each kernel group while enabled.
  * Categories: 0 GS fine level, 1 GS coarser levels, 2 K-apply/residual fine, 3 K-apply coarser, 4 grid
  * transfer, 5 coarsest triangular solves, 6 coarsest factorisation, 7 Krylov vector kernels, 8 set-up,
- * 9 gradients, 10 layout conversion. */
-/* Kernel-variant switches for A/B tests and profiling (no reference counterpart; defaults are the production
- * choice and can also be preset through the environment variables PDEOP_GS_PIPE / PDEOP_CHAIN):
+ * 9 gradients, 10 layout conversion.  pdeop_plan_profile_collect waits for the recorded events and returns the
+ * number of categories.  pdeop_launch_count: kernels launched by the library so far (process-wide statistic). */
+int pdeop_plan_profile_enable(pdeop_plan* plan, int on);
+int pdeop_plan_profile_collect(pdeop_plan* plan, double* ms_per_category, long long* count_per_category, int ncat);
+long long pdeop_launch_count(void);
+/* Kernel-variant switch of ONE plan, for A/B tests and profiling (no reference counterpart):
  *   key 0 "gs_pipe": 0 unsplit cluster Gauss-Seidel kernel on every level, 1 software-pipelined kernel on every
  *                    level, 2 (default) pipelined kernel on the latency-bound levels only
- *   key 1 "chain"  : 1 (default) persistent chain kernels for the coarsest triangular solves where they apply,
- *                    0 one launch per block row.  Takes effect at the next operator set-up.
- * Returns 0, or 1 for an unknown key. */
-int pdeop_set_tuning(int key, int value);
-void pdeop_profile_enable(int on);
-int pdeop_profile_collect(double* ms_per_category, long long* count_per_category, int ncat);
-long long pdeop_launch_count(void);
+ *   key 1 "chain"  : read-only (pdeop_plan_get_tuning); chosen at creation, see pdeop_plan_opts.chain
+ * Returns 0, or nonzero with pdeop_last_error(). */
+int pdeop_plan_set_tuning(pdeop_plan* plan, int key, int value);
+int pdeop_plan_get_tuning(const pdeop_plan* plan, int key, int* value);
 
 #ifdef __cplusplus
 }

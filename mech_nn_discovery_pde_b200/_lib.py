@@ -22,6 +22,11 @@ Q_DIM0 = 16
 STAGE_APPLY_K, STAGE_GS, STAGE_RESTRICT, STAGE_PROLONG, STAGE_VCYCLE, STAGE_COARSE_SOLVE, STAGE_ATB = range(7)
 
 
+class PlanOpts(ctypes.Structure):
+    """pdeop_plan_opts: creation-time options of a plan."""
+    _fields_ = [("evolution", c_int), ("chain", c_int), ("gs_pipe", c_int), ("reserved", c_int * 5)]
+
+
 class SolverCfg(ctypes.Structure):
     _fields_ = [("gs_pre", c_int), ("gs_post", c_int), ("mg_steps", c_int), ("max_iter", c_int),
                 ("restart", c_int), ("atol", ctypes.c_double), ("gs_variant", c_int)]
@@ -30,9 +35,11 @@ class SolverCfg(ctypes.Structure):
 EXPORTS = [
     "pdeop_plan_create", "pdeop_plan_destroy", "pdeop_plan_query", "pdeop_last_error", "pdeop_backend_name",
     "pdeop_mg_forward", "pdeop_mg_backward", "pdeop_dense_forward", "pdeop_dense_backward", "pdeop_mg_setup",
-    "pdeop_stage", "pdeop_fgmres", "pdeop_profile_enable", "pdeop_profile_collect", "pdeop_launch_count",
-    "pdeop_set_tuning",
+    "pdeop_stage", "pdeop_fgmres", "pdeop_plan_profile_enable", "pdeop_plan_profile_collect", "pdeop_launch_count",
+    "pdeop_plan_set_tuning", "pdeop_plan_get_tuning", "pdeop_plan_create_ex",
 ]
+
+TUNING_KEYS = {"gs_pipe": 0, "chain": 1}
 
 PROFILE_CATEGORIES = ["gs_fine", "gs_coarse", "apply_fine", "apply_coarse", "transfer", "coarse_solve", "factor",
                       "krylov", "setup", "grads", "layout"]
@@ -66,6 +73,8 @@ class PdeopLibrary:
         d.pdeop_backend_name.restype = ctypes.c_char_p
         d.pdeop_plan_create.argtypes = [c_int, ctypes.POINTER(c_int), c_int, c_int, c_int, c_int, c_int,
                                         ctypes.POINTER(c_int), ctypes.POINTER(c_void_p)]
+        d.pdeop_plan_create_ex.argtypes = [c_int, ctypes.POINTER(c_int), c_int, c_int, c_int, c_int, c_int,
+                                           ctypes.POINTER(c_int), ctypes.POINTER(PlanOpts), ctypes.POINTER(c_void_p)]
         d.pdeop_plan_destroy.argtypes = [c_void_p]
         d.pdeop_plan_destroy.restype = None
         d.pdeop_plan_query.argtypes = [c_void_p, c_int, c_int, ctypes.POINTER(ctypes.c_longlong)]
@@ -78,45 +87,55 @@ class PdeopLibrary:
         d.pdeop_mg_setup.argtypes = [c_void_p, c_void_p] + [PP] * 3 + [c_void_p] * 4
         d.pdeop_stage.argtypes = [c_void_p, CFG, c_int, c_int, c_int] + [c_void_p] * 6
         d.pdeop_fgmres.argtypes = [c_void_p, CFG, c_int] + [c_void_p] * 7
-        d.pdeop_profile_enable.argtypes = [c_int]
-        d.pdeop_profile_enable.restype = None
-        d.pdeop_profile_collect.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong), c_int]
+        d.pdeop_plan_profile_enable.argtypes = [c_void_p, c_int]
+        d.pdeop_plan_profile_collect.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_double),
+                                                 ctypes.POINTER(ctypes.c_longlong), c_int]
+        d.pdeop_plan_set_tuning.argtypes = [c_void_p, c_int, c_int]
+        d.pdeop_plan_get_tuning.argtypes = [c_void_p, c_int, ctypes.POINTER(c_int)]
         d.pdeop_launch_count.restype = ctypes.c_longlong
         self.backend = d.pdeop_backend_name().decode()
 
-    def profile_enable(self, on=True):
-        self.dll.pdeop_profile_enable(1 if on else 0)
+    def profile_enable(self, plan, on=True):
+        self.check(self.dll.pdeop_plan_profile_enable(plan, 1 if on else 0))
 
-    def profile_collect(self):
-        """{category: (total_ms, launches_groups)} since profile_enable; waits for the recorded events."""
+    def profile_collect(self, plan):
+        """{category: (total_ms, kernel groups)} of one plan since profile_enable; waits for the recorded events."""
         n = len(PROFILE_CATEGORIES)
         ms = (ctypes.c_double * n)()
         cnt = (ctypes.c_longlong * n)()
-        self.dll.pdeop_profile_collect(ms, cnt, n)
+        self.dll.pdeop_plan_profile_collect(plan, ms, cnt, n)
         return {PROFILE_CATEGORIES[i]: (float(ms[i]), int(cnt[i])) for i in range(n)}
 
     def launch_count(self):
         return int(self.dll.pdeop_launch_count())
 
-    def set_tuning(self, key, value):
-        """Kernel-variant switch (pdeop.h: pdeop_set_tuning); key 'gs_pipe' or 'chain'."""
-        k = {"gs_pipe": 0, "chain": 1}[key]
-        if self.dll.pdeop_set_tuning(k, int(value)) != 0:
-            raise PdeopError("unknown tuning key")
+    def set_tuning(self, plan, key, value):
+        """Kernel-variant switch of one plan (pdeop.h: pdeop_plan_set_tuning); key 'gs_pipe'."""
+        self.check(self.dll.pdeop_plan_set_tuning(plan, TUNING_KEYS[key], int(value)))
+
+    def get_tuning(self, plan, key):
+        out = c_int()
+        self.check(self.dll.pdeop_plan_get_tuning(plan, TUNING_KEYS[key], ctypes.byref(out)))
+        return int(out.value)
 
     def check(self, rc):
         if rc != 0:
             raise PdeopError("pdeop: " + self.dll.pdeop_last_error().decode())
 
-    def plan_create(self, dims, order, batch, n_grid, downsample_first, iv_desc):
+    def plan_create(self, dims, order, batch, n_grid, downsample_first, iv_desc, evolution=False, chain=None,
+                    gs_pipe=None):
         d = len(dims)
         dims_a = (c_int * d)(*[int(v) for v in dims])
         n_iv = len(iv_desc[0]) if iv_desc else 0
         flat = [int(v) for lvl in iv_desc for spec in lvl for v in spec]
         iv_a = (c_int * max(len(flat), 1))(*flat)
         out = c_void_p()
-        self.check(self.dll.pdeop_plan_create(d, dims_a, order, batch, n_grid, int(bool(downsample_first)), n_iv,
-                                              iv_a, ctypes.byref(out)))
+        opts = PlanOpts()
+        opts.evolution = int(bool(evolution))
+        opts.chain = -1 if chain is None else int(bool(chain))
+        opts.gs_pipe = -1 if gs_pipe is None else int(gs_pipe)
+        self.check(self.dll.pdeop_plan_create_ex(d, dims_a, order, batch, n_grid, int(bool(downsample_first)), n_iv,
+                                                 iv_a, ctypes.byref(opts), ctypes.byref(out)))
         return out
 
     def plan_destroy(self, plan):

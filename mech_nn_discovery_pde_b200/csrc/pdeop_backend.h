@@ -23,7 +23,12 @@ void be_event_destroy(void* ev);
 void be_event_record(void* ev, stream_t st);
 float be_event_elapsed_ms(void* start, void* stop);  // waits for `stop`
 long long be_launch_count();
-int be_set_tuning(int key, int value);   // see pdeop_set_tuning
+// device the calling thread is bound to (cudaGetDevice), -1 without one; be_set_device binds it
+int be_current_device();
+// process defaults of the per-plan kernel-variant switches (environment variables PDEOP_GS_PIPE / PDEOP_CHAIN,
+// read when a plan is created; afterwards the plan's own copy is what every call uses)
+int be_default_gs_pipe();
+bool be_default_chain();
 
 void be_build_tables(stream_t st, const LevelDev& L, int B, const double* cv, const double* fv, const double* bv,
                      double* T);
@@ -39,8 +44,10 @@ void be_apply_k(stream_t st, const LevelDev& L, int B, const double* T, const do
 // nsweeps lexicographic Gauss-Seidel sweeps, in place.  variant 0: production kernel; 1: one launch per
 // hyperplane step (test cross-check).  stash: B * stash_stride doubles of scratch for the production kernel
 // (stash_stride >= be_gs_stash_doubles(L)).
+// gs_pipe: 0 unsplit cluster kernel, 1 software-pipelined kernel, 2 pipelined on the latency-bound levels only
 void be_gs(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, const double* dinv,
-           const double* b, double* x, double* stash, size_t stash_stride, int nsweeps, const int* done, int variant);
+           const double* b, double* x, double* stash, size_t stash_stride, int nsweeps, const int* done, int variant,
+           int gs_pipe);
 // per-instance stash size: 8 doubles per point of the busiest step, rounded up to whole rounds of the largest
 // cluster (8 CTAs x 512 threads)
 inline size_t be_gs_stash_doubles(const LevelDev& L) { return 8 * ((size_t)L.G + 4096); }
@@ -70,13 +77,13 @@ inline ChainLayout be_chain_layout(int n, int bw) {
     c.use = (n % 2 == 0) && c.nblk >= 8 && c.nbmax + 1 <= 32;   // vector window of nbmax+1 blocks must fit shared memory
     return c;
 }
-// true when be_cholesky / be_chol_solve will use the chain solver for (n, bw): the dense n x n array is then only
-// needed during operator set-up (the solves read the compact scaled band in the Linv area)
-bool be_chain_active(int n, int bw);
-inline size_t be_chol_linv_doubles(int B, int n, int bw) {
+// use_chain (decided ONCE per plan: layout and solver choice come from the same snapshot): be_cholesky builds and
+// be_chol_solve reads the compact scaled band in the Linv area; the dense n x n array is then only needed during
+// operator set-up
+inline size_t be_chol_linv_doubles(int B, int n, int bw, bool use_chain) {
     const ChainLayout c = be_chain_layout(n, bw);
     size_t tot = 2 * (size_t)B * c.nblk * kSolveBlk * kSolveBlk;
-    if (c.use) tot += 64 + (size_t)B * n * ((size_t)c.pw + c.pwt);
+    if (c.use && use_chain) tot += 64 + (size_t)B * n * ((size_t)c.pw + c.pwt);
     return tot;
 }
 
@@ -84,11 +91,11 @@ inline size_t be_chol_linv_doubles(int B, int n, int bw) {
 // (bw = half-bandwidth of the matrix in the dense ordering; nothing outside the band is touched)
 // Linv: be_chol_linv_doubles(B, n, bw) doubles receiving the inverses of the diagonal blocks of L, their transposes
 // and, when the chain solver applies, the block-scaled band W = blockdiag(L_kk)^-1 L in two compact layouts
-void be_cholesky(stream_t st, int B, int n, int bw, double* Kd, double* Linv, FgmresState* state);
+void be_cholesky(stream_t st, int B, int n, int bw, double* Kd, double* Linv, FgmresState* state, bool use_chain);
 // out = (L L^T)^-1 rhs for the dense system of level L (n = M*G); rhs/out in wave/planar layout, the
 // factor in band ordering; work: 2*B*n doubles
 void be_chol_solve(stream_t st, const LevelDev& L, int B, const double* Lf, const double* Linv, const double* rhs,
-                   double* out, double* work, const int* done);
+                   double* out, double* work, const int* done, bool use_chain);
 void be_grads(stream_t st, const LevelDev& L, int B, const double* coef, const double* rhs_nat, const double* cv,
               const double* fv, const double* bv, const double* x, const double* dz, double* d_coeffs,
               double* d_rhs, double* d_iv, double* d_cv, double* d_fv, double* d_bv);

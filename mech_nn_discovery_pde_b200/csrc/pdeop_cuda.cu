@@ -16,6 +16,11 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "pdeop_backend.h"
 #include "pdeop_elem.h"
 #include "pdeop_lstsq.h"
@@ -37,10 +42,35 @@ static thread_local cudaError_t g_cuda_err = cudaSuccess;
 static inline void note(cudaError_t e) {
     if (e != cudaSuccess && g_cuda_err == cudaSuccess) g_cuda_err = e;
 }
-static long long g_launches = 0;   // kernels launched by this library (bench.py reports it)
+// statistics only (bench.py reports it): kernels launched by this library, all plans and threads
+static std::atomic<long long> g_launches{0};
 #define PDEOP_LAUNCH_CHECK() note(cudaGetLastError())
-#define PDEOP_COUNT(k) (g_launches += (k))
-long long be_launch_count() { return g_launches; }
+#define PDEOP_COUNT(k) (g_launches.fetch_add((k), std::memory_order_relaxed))
+long long be_launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+int be_current_device() {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return dev;
+}
+
+// Per-device caches (a process may drive several GPUs, one plan each): SM count, the largest dynamic shared-memory
+// size already granted to a kernel, and cluster-occupancy answers.  Keyed by (device, kernel); guarded by a mutex
+// because plans on different devices may be driven from different host threads.
+static std::mutex g_cache_mu;
+static std::map<std::pair<int, const void*>, size_t> g_smem_granted;
+static void ensure_dyn_smem(const void* kern, size_t bytes) {
+    const int dev = be_current_device();
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    size_t& cur = g_smem_granted[{dev, kern}];
+    if (bytes > cur) {
+        note(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        cur = bytes;
+    }
+}
 
 void* be_event_create() {
     cudaEvent_t e = nullptr;
@@ -556,58 +586,74 @@ __global__ void __launch_bounds__(kThreads) k_gs_step(LevelDev L, const double* 
                                 b + o, x + o, h0 + j);
 }
 
-static int g_num_sms = 0;
 static int num_sms() {
-    if (!g_num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
+    static std::map<int, int> per_dev;
+    const int dev = be_current_device();
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    int& n = per_dev[dev];
+    if (!n) {
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev < 0 ? 0 : dev);
+        if (n <= 0) n = 148;
     }
-    return g_num_sms;
+    return n;
 }
 
-// tuning switch (read once): PDEOP_GS_SMEM = 0 disables the shared-memory staging of the tables (A/B testing)
-// PDEOP_GS_SINGLE = n: levels whose busiest step has at most n*512 points run with one CTA per instance
-static int g_gs_threads = 0, g_gs_smem = 1, g_gs_single = 0, g_gs_pipe = 1;
-static void gs_tuning() {
-    if (g_gs_threads) return;
-    // 128 registers/thread; 256/384/1024-thread variants were measured and are not faster, and 768 threads
-    // (80 registers, 300 bytes of spills) take 4.2 instead of 2.9 ms per fine-level call
-    g_gs_threads = 512;
-    const char* m = getenv("PDEOP_GS_SMEM");
-    g_gs_smem = (m && atoi(m) == 0) ? 0 : 1;
-    const char* sg = getenv("PDEOP_GS_SINGLE");
-    g_gs_single = sg ? atoi(sg) : 0;
-    // PDEOP_GS_PIPE: 0 = unsplit cluster kernel everywhere, 1 = software-pipelined kernel everywhere,
-    // default (2) = pipelined kernel on the latency-bound levels (busiest step <= 3 points per thread), where it
-    // was measured faster (B200: 32x32x32 1.00 vs 1.04 ms, 32x16x16 0.48 vs 0.50 ms per 5 sweeps, batch 32);
-    // on throughput-bound levels (32x64x64: 3.30 vs 3.08 ms) the stash round trip costs more than the overlap gains
-    const char* pp = getenv("PDEOP_GS_PIPE");
-    g_gs_pipe = pp ? atoi(pp) : 2;
+// Process defaults, read once from the environment and never written afterwards:
+//   PDEOP_GS_SMEM = 0 disables the shared-memory staging of the tables (A/B testing)
+//   PDEOP_GS_SINGLE = n: levels whose busiest step has at most n*512 points run with one CTA per instance
+//   PDEOP_GS_PIPE: default of the per-plan "gs_pipe" switch: 0 = unsplit cluster kernel everywhere, 1 = software-
+//     pipelined kernel everywhere, 2 (default) = pipelined kernel on the latency-bound levels (busiest step <= 3
+//     points per thread), where it was measured faster (B200: 32x32x32 1.00 vs 1.04 ms, 32x16x16 0.48 vs 0.50 ms per
+//     5 sweeps, batch 32); on throughput-bound levels (32x64x64: 3.30 vs 3.08 ms) the stash round trip costs more
+//     than the overlap gains
+struct GsEnv {
+    int threads, smem, single, pipe;
+    GsEnv() {
+        // 128 registers/thread; 256/384/1024-thread variants were measured and are not faster, and 768 threads
+        // (80 registers, 300 bytes of spills) take 4.2 instead of 2.9 ms per fine-level call
+        threads = 512;
+        const char* m = getenv("PDEOP_GS_SMEM");
+        smem = (m && atoi(m) == 0) ? 0 : 1;
+        const char* sg = getenv("PDEOP_GS_SINGLE");
+        single = sg ? atoi(sg) : 0;
+        const char* pp = getenv("PDEOP_GS_PIPE");
+        pipe = pp ? atoi(pp) : 2;
+    }
+};
+static const GsEnv& gs_env() {
+    static const GsEnv e;
+    return e;
 }
+int be_default_gs_pipe() { return gs_env().pipe; }
 
 // Shrinks the cluster size until all instances' clusters are co-resident (one wave): a cluster needs its CTAs on
 // SMs of one GPC, so e.g. 16 clusters of 8 do not fit a B200 although 128 SMs would suffice (measured: 2 waves,
 // 3.35 ms vs 3.10 ms for 32 clusters of 4 with twice the work).  Results cached per (kernel, smem, cluster size).
 template <class K>
 static void fit_cluster_wave(cudaLaunchConfig_t& cfg, K kern, int B) {
-    static int cache_smem[4] = {-1, -1, -1, -1}, cache_max[4] = {0, 0, 0, 0};   // index log2(cluster size)
+    // answers of cudaOccupancyMaxActiveClusters per (device, kernel, shared memory, cluster size)
+    static std::map<std::tuple<int, const void*, size_t, unsigned>, int> cache;
+    const int dev = be_current_device();
     unsigned& cs = cfg.attrs[0].val.clusterDim.x;
     while (cs > 1) {
-        int lg = 0;
-        while ((1u << lg) < cs) ++lg;
-        if (cache_smem[lg] != (int)cfg.dynamicSmemBytes) {
-            int nmax = 0;
-            cfg.gridDim = dim3((unsigned)(B * cs));
-            if (cudaOccupancyMaxActiveClusters(&nmax, kern, &cfg) != cudaSuccess) {
-                cudaGetLastError();
-                nmax = B;   // cannot tell: keep the size
+        const auto key = std::make_tuple(dev, (const void*)kern, (size_t)cfg.dynamicSmemBytes, cs);
+        int nmax;
+        {
+            std::lock_guard<std::mutex> lk(g_cache_mu);
+            auto it = cache.find(key);
+            if (it == cache.end()) {
+                nmax = 0;
+                cfg.gridDim = dim3((unsigned)(B * cs));
+                if (cudaOccupancyMaxActiveClusters(&nmax, kern, &cfg) != cudaSuccess) {
+                    cudaGetLastError();
+                    nmax = 1 << 30;   // cannot tell: keep the size
+                }
+                cache[key] = nmax;
+            } else {
+                nmax = it->second;
             }
-            cache_smem[lg] = (int)cfg.dynamicSmemBytes;
-            cache_max[lg] = nmax;
         }
-        if (cache_max[lg] >= B) break;
+        if (nmax >= B) break;
         cs /= 2;
     }
     cfg.gridDim = dim3((unsigned)(B * cs));
@@ -620,11 +666,7 @@ static void launch_gs_inst(cudaLaunchConfig_t& cfg, const LevelDev& L, const dou
     size_t smem = 0;
     if (PS > 0) {
         smem = (size_t)D * kTabEntries * PS * sizeof(double) + ((size_t)(L.S + 8) * L.N[0] + 8 + L.S + 1) * sizeof(int);
-        static size_t set_for = 0;   // per instantiation
-        if (smem > set_for) {
-            note(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            set_for = smem;
-        }
+        ensure_dyn_smem((const void*)kern, smem);
     }
     cfg.dynamicSmemBytes = smem;
     if (!SINGLE) fit_cluster_wave(cfg, kern, (int)(cfg.gridDim.x / cfg.attrs[0].val.clusterDim.x));
@@ -639,13 +681,7 @@ static void launch_gs_pipe(cudaLaunchConfig_t& cfg, const LevelDev& L, const dou
     size_t smem = (size_t)kStashSlots * THREADS * sizeof(double);
     if (PS > 0)
         smem += (size_t)D * kTabEntries * PS * sizeof(double) + ((size_t)(L.S + 8) * L.N[0] + 8 + L.S + 1) * sizeof(int);
-    {
-        static size_t set_for = 0;   // per instantiation
-        if (smem > set_for) {
-            note(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            set_for = smem;
-        }
-    }
+    ensure_dyn_smem((const void*)kern, smem);
     cfg.dynamicSmemBytes = smem;
     if (!SINGLE) fit_cluster_wave(cfg, kern, (int)(cfg.gridDim.x / cfg.attrs[0].val.clusterDim.x));
     note(cudaLaunchKernelEx(&cfg, kern, L, T, coef, dinv, b, x, stash, stash_stride, nsweeps, done));
@@ -654,14 +690,14 @@ static void launch_gs_pipe(cudaLaunchConfig_t& cfg, const LevelDev& L, const dou
 template <int D>
 static void launch_gs_cluster(cudaStream_t s, const LevelDev& L, int B, const double* T, const double* coef,
                               const double* dinv, const double* b, double* x, double* stash, size_t stash_stride,
-                              int nsweeps, const int* done) {
-    gs_tuning();
-    const int threads = g_gs_threads;
+                              int nsweeps, const int* done, int gs_pipe) {
+    const GsEnv& env = gs_env();
+    const int threads = env.threads;
     const int per_sm = 1;   // CTAs per SM (register-limited: 128 regs/thread x 512 threads)
     int maxn = L.N[0] > L.N[1] ? L.N[0] : L.N[1];
     maxn = (maxn > L.N[2] ? maxn : L.N[2]) + 2 * kTabPad;
     int ps = 0;
-    if (g_gs_smem) {
+    if (env.smem) {
         if (maxn <= 40) ps = 40;
         else if (maxn <= 72) ps = 72;
         else if (maxn <= 136) ps = 136;
@@ -682,7 +718,7 @@ static void launch_gs_cluster(cudaStream_t s, const LevelDev& L, int B, const do
     int fit = per_sm * num_sms() / (B > 0 ? B : 1);
     int csize = 1;
     while (csize * 2 <= 8 && csize * 2 <= fit && csize < want) csize *= 2;
-    const bool single = csize == 1 || want <= g_gs_single;
+    const bool single = csize == 1 || want <= env.single;
     if (single) csize = 1;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -713,7 +749,7 @@ static void launch_gs_cluster(cudaStream_t s, const LevelDev& L, int B, const do
         default: launch_gs_pipe<D, 512, 0, SG>(cfg, L, T, coef, dinv, b, x, stash, stash_stride, nsweeps, done); break;    \
     }
     // (2-D grids: the unsplit kernel is faster -- Burgers 256x256, batch 64: 78.1 vs 74.2 solves/s)
-    const bool use_pipe = stash && (g_gs_pipe == 1 || (g_gs_pipe == 2 && D == 3 && want <= 3 * csize));
+    const bool use_pipe = stash && (gs_pipe == 1 || (gs_pipe == 2 && D == 3 && want <= 3 * csize));
     if (use_pipe) {
         if (single) { PDEOP_GS_PIPE_DISPATCH(true) } else { PDEOP_GS_PIPE_DISPATCH(false) }
     } else if (single) { PDEOP_GS_DISPATCH(true) } else { PDEOP_GS_DISPATCH(false) }
@@ -740,13 +776,14 @@ void be_dinv(stream_t st, const LevelDev& L, int B, const double* T, const doubl
 }
 
 void be_gs(stream_t st, const LevelDev& L, int B, const double* T, const double* coef, const double* dinv,
-           const double* b, double* x, double* stash, size_t stash_stride, int nsweeps, const int* done, int variant) {
+           const double* b, double* x, double* stash, size_t stash_stride, int nsweeps, const int* done, int variant,
+           int gs_pipe) {
     if (nsweeps <= 0) return;
     cudaStream_t s = (cudaStream_t)st;
     if (variant == 0) {
-        if (L.D == 1) launch_gs_cluster<1>(s, L, B, T, coef, dinv, b, x, stash, stash_stride, nsweeps, done);
-        else if (L.D == 2) launch_gs_cluster<2>(s, L, B, T, coef, dinv, b, x, stash, stash_stride, nsweeps, done);
-        else launch_gs_cluster<3>(s, L, B, T, coef, dinv, b, x, stash, stash_stride, nsweeps, done);
+        if (L.D == 1) launch_gs_cluster<1>(s, L, B, T, coef, dinv, b, x, stash, stash_stride, nsweeps, done, gs_pipe);
+        else if (L.D == 2) launch_gs_cluster<2>(s, L, B, T, coef, dinv, b, x, stash, stash_stride, nsweeps, done, gs_pipe);
+        else launch_gs_cluster<3>(s, L, B, T, coef, dinv, b, x, stash, stash_stride, nsweeps, done, gs_pipe);
         PDEOP_COUNT(1);
         PDEOP_LAUNCH_CHECK();
         return;
@@ -1445,31 +1482,15 @@ static void chain_arrays(const ChainLayout& cl, int B, int n, double* Linv, doub
     *Wc = p;
     *WTc = p + (size_t)B * n * cl.pw;
 }
-static int g_chain = -1;
-static bool chain_enabled() {
-    if (g_chain < 0) {
+bool be_default_chain() {
+    static const bool on = [] {
         const char* e = getenv("PDEOP_CHAIN");   // 0: per-block-row launches (A/B testing)
-        g_chain = (e && atoi(e) == 0) ? 0 : 1;
-    }
-    return g_chain != 0;
+        return !(e && atoi(e) == 0);
+    }();
+    return on;
 }
 
-bool be_chain_active(int n, int bw) { return be_chain_layout(n, bw).use && chain_enabled(); }
-
-int be_set_tuning(int key, int value) {
-    if (key == 0) {
-        gs_tuning();
-        g_gs_pipe = value;
-        return 0;
-    }
-    if (key == 1) {
-        g_chain = value ? 1 : 0;
-        return 0;
-    }
-    return 1;
-}
-
-void be_cholesky(stream_t st, int B, int n, int bw, double* Kd, double* Linv, FgmresState* state) {
+void be_cholesky(stream_t st, int B, int n, int bw, double* Kd, double* Linv, FgmresState* state, bool use_chain) {
     cudaStream_t s = (cudaStream_t)st;
     const size_t strideA = (size_t)n * n;
     for (int K0 = 0; K0 < n; K0 += kOuter) {
@@ -1498,16 +1519,12 @@ void be_cholesky(stream_t st, int B, int n, int bw, double* Kd, double* Linv, Fg
     k_trtri<<<dim3(nblk, B), kSolveBlk, 0, s>>>(n, Kd, strideA, Linv, nblk);
     PDEOP_COUNT(1);
     const ChainLayout cl = be_chain_layout(n, bw);
-    if (cl.use && chain_enabled()) {
+    if (cl.use && use_chain) {
         double *Wc, *WTc;
         chain_arrays(cl, B, n, Linv, &Wc, &WTc);
         note(cudaMemsetAsync(WTc, 0, (size_t)B * n * cl.pwt * sizeof(double), s));   // entries W does not store
-        static bool attr_set = false;
         const int smem = kSolveBlk * kWTile * (int)sizeof(double);
-        if (!attr_set) {
-            note(cudaFuncSetAttribute(k_make_w, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr_set = true;
-        }
+        ensure_dyn_smem((const void*)k_make_w, smem);
         const double* LinvT = Linv + (size_t)B * nblk * kSolveBlk * kSolveBlk;
         k_make_w<<<dim3(cdiv(cl.pw, kWTile), nblk - 1, B), kSolveBlk, smem, s>>>(n, nblk, cl.pw, cl.pwt, Kd, strideA, LinvT,
                                                                                 Wc, WTc);
@@ -2038,11 +2055,7 @@ static void launch_chain(cudaStream_t s, int dir, int B, int n, const ChainLayou
     int ch = kChainCHMax;
     while (ch > 64 && chain_smem_bytes(nw, ch) > (size_t)227 * 1024) ch -= 32;
     const size_t smem = chain_smem_bytes(nw, ch);
-    static size_t set_for = 0;
-    if (smem > set_for) {
-        note(cudaFuncSetAttribute(k_band_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        set_for = smem;
-    }
+    ensure_dyn_smem((const void*)k_band_chain, smem);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(B * kChainCta));
@@ -2061,7 +2074,7 @@ static void launch_chain(cudaStream_t s, int dir, int B, int n, const ChainLayou
 }
 
 void be_chol_solve(stream_t st, const LevelDev& L, int B, const double* Lf, const double* Linv, const double* rhs,
-                   double* out, double* work, const int* done) {
+                   double* out, double* work, const int* done, bool use_chain) {
     cudaStream_t s = (cudaStream_t)st;
     const int n = L.M * L.G;
     const int bw = L.bw;
@@ -2073,7 +2086,7 @@ void be_chol_solve(stream_t st, const LevelDev& L, int B, const double* Lf, cons
     k_to_band<<<dim3(cdiv(L.G, kThreads), B), kThreads, 0, s>>>(L, rhs, rb, done);
     PDEOP_COUNT(1);
     const ChainLayout cl = be_chain_layout(n, bw);
-    if (cl.use && chain_enabled()) {
+    if (cl.use && use_chain) {
         // L^-1 = Wt^-1 D^-1, L^-T = D^-T Wt^-T: block-diagonal product, two chains, block-diagonal product
         double *Wc, *WTc;
         chain_arrays(cl, B, n, const_cast<double*>(Linv), &Wc, &WTc);

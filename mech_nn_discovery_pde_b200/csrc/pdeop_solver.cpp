@@ -28,43 +28,40 @@ enum ProfCat {
     PC_KRYLOV, PC_SETUP, PC_GRADS, PC_LAYOUT, PC_COUNT
 };
 struct ProfRec { int cat; void* a; void* b; };
-static bool g_prof_on = false;
-static std::vector<ProfRec> g_prof_recs;
-static std::vector<void*> g_prof_pool;
-static void* prof_event() {
-    if (!g_prof_pool.empty()) { void* e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
-    return be_event_create();
-}
-struct ProfScope {
-    int cat; void* a = nullptr; stream_t st;
-    ProfScope(int c, stream_t s) : cat(c), st(s) {
-        if (g_prof_on) { a = prof_event(); be_event_record(a, st); }
+// per-plan instrumentation state (a plan is driven by one host thread at a time; two plans never share state)
+struct ProfState {
+    bool on = false;
+    std::vector<ProfRec> recs;
+    std::vector<void*> pool;
+    void* event() {
+        if (!pool.empty()) { void* e = pool.back(); pool.pop_back(); return e; }
+        return be_event_create();
     }
-    ~ProfScope() {
-        if (a) { void* b = prof_event(); be_event_record(b, st); g_prof_recs.push_back({cat, a, b}); }
+    ~ProfState() {
+        for (auto& r : recs) { be_event_destroy(r.a); be_event_destroy(r.b); }
+        for (void* e : pool) be_event_destroy(e);
     }
 };
-extern "C" void pdeop_profile_enable(int on) {
-    g_prof_on = on != 0;
-    for (auto& r : g_prof_recs) { g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b); }
-    g_prof_recs.clear();
-}
-extern "C" int pdeop_profile_collect(double* ms, long long* counts, int ncat) {
-    for (int i = 0; i < ncat; ++i) { ms[i] = 0.0; counts[i] = 0; }
-    for (auto& r : g_prof_recs) {
-        if (r.cat < ncat) { ms[r.cat] += be_event_elapsed_ms(r.a, r.b); counts[r.cat] += 1; }
-        g_prof_pool.push_back(r.a);
-        g_prof_pool.push_back(r.b);
+struct ProfScope {
+    ProfState* ps; int cat; void* a = nullptr; stream_t st;
+    ProfScope(ProfState& p, int c, stream_t s) : ps(&p), cat(c), st(s) {
+        if (ps->on) { a = ps->event(); be_event_record(a, st); }
     }
-    g_prof_recs.clear();
-    return PC_COUNT;
-}
+    ~ProfScope() {
+        if (a) { void* b = ps->event(); be_event_record(b, st); ps->recs.push_back({cat, a, b}); }
+    }
+};
 extern "C" long long pdeop_launch_count(void) { return be_launch_count(); }
-extern "C" int pdeop_set_tuning(int key, int value) { return be_set_tuning(key, value); }
 
 static int fail(const std::string& msg) {
     g_err = msg;
     return 1;
+}
+
+static int check_backend() {
+    char buf[512];
+    if (be_last_error(buf, sizeof(buf))) return fail(std::string("backend error: ") + buf);
+    return 0;
 }
 
 struct LevelHost {
@@ -84,6 +81,12 @@ struct pdeop_plan {
     // The dense nc x nc array lives in the (per-layer, reused) scratch buffer instead of the (per-forward-call)
     // persist buffer when the chain solver is active: it is then dead after operator set-up.
     bool kd_in_scratch = false;
+    // Kernel-variant choices, fixed when the plan is created (the buffer layout depends on use_chain, so the
+    // layout and the solver choice come from the same snapshot); gs_pipe may be changed per plan for A/B tests.
+    bool use_chain = true;
+    int gs_pipe = 2;
+    int device = -1;   // CUDA device the plan's tables live on; every entry point checks it is current
+    ProfState prof;
 };
 
 template <class T>
@@ -206,12 +209,22 @@ static int build_level(pdeop_plan* pl, LevelHost& lh, const int* dims, int n_iv,
 
 extern "C" int pdeop_plan_create(int d, const int* dims, int order, int batch, int n_grid, int downsample_first,
                                  int n_iv, const int* iv_desc, pdeop_plan** out) {
+    return pdeop_plan_create_ex(d, dims, order, batch, n_grid, downsample_first, n_iv, iv_desc, nullptr, out);
+}
+
+extern "C" int pdeop_plan_create_ex(int d, const int* dims, int order, int batch, int n_grid, int downsample_first,
+                                    int n_iv, const int* iv_desc, const pdeop_plan_opts* opts, pdeop_plan** out) {
     if (!out) return fail("null out");
     *out = nullptr;
     if (d < 1 || d > 3) return fail("dimension must be 1, 2 or 3");
     if (order != 2) return fail("only total order 2 is implemented");
     if (batch < 1 || n_grid < 1) return fail("batch and n_grid must be positive");
+    if (batch > 65535) return fail("batch above 65535 not supported (instances map to gridDim.y)");
     pdeop_plan* pl = new pdeop_plan();
+    pl->device = be_current_device();
+    pl->gs_pipe = (opts && opts->gs_pipe >= 0) ? opts->gs_pipe : be_default_gs_pipe();
+    if (pl->gs_pipe > 2) { delete pl; return fail("gs_pipe must be 0, 1 or 2"); }
+    const bool want_chain = (opts && opts->chain >= 0) ? opts->chain != 0 : be_default_chain();
     pl->D = d;
     pl->M = 1 + 2 * d;
     pl->B = batch;
@@ -241,11 +254,16 @@ extern "C" int pdeop_plan_create(int d, const int* dims, int order, int batch, i
     const LevelDev& Lc = pl->lev[n_grid - 1].dev;
     pl->nc = Lc.M * Lc.G;
     pl->off_Kd = poff;
-    pl->kd_in_scratch = be_chain_active(pl->nc, Lc.bw);
+    pl->use_chain = be_chain_layout(pl->nc, Lc.bw).use && want_chain;
+    pl->kd_in_scratch = pl->use_chain;
     if (!pl->kd_in_scratch) poff += (size_t)batch * pl->nc * pl->nc;
     pl->off_Linv = poff;
-    poff += be_chol_linv_doubles(batch, pl->nc, Lc.bw);   // inverse diagonal blocks (+ transposes, + scaled band)
+    poff += be_chol_linv_doubles(batch, pl->nc, Lc.bw, pl->use_chain);   // inverse diagonal blocks (+ transposes, + scaled band)
     pl->persist_doubles = poff;
+    if (check_backend()) {   // a failed table allocation or upload
+        pdeop_plan_destroy(pl);
+        return 1;
+    }
     *out = pl;
     return 0;
 }
@@ -336,14 +354,59 @@ extern "C" int pdeop_plan_query(const pdeop_plan* pl, int what, int level, long 
     return fail("unknown query");
 }
 
-extern "C" const char* pdeop_last_error(void) { return g_err.c_str(); }
-extern "C" const char* pdeop_backend_name(void) { return be_name(); }
-
-static int check_backend() {
-    char buf[512];
-    if (be_last_error(buf, sizeof(buf))) return fail(std::string("backend error: ") + buf);
+// every compute entry point: the plan's tables live on one device, which must be the calling thread's current one
+static int check_plan(const pdeop_plan* pl) {
+    if (!pl) return fail("null plan");
+    const int cur = be_current_device();
+    if (cur != pl->device) {
+        char buf[160];
+        snprintf(buf, sizeof(buf), "plan was created on device %d but device %d is current; cudaSetDevice (torch.cuda."
+                 "device) to the plan's device before calling", pl->device, cur);
+        return fail(buf);
+    }
     return 0;
 }
+
+extern "C" int pdeop_plan_set_tuning(pdeop_plan* pl, int key, int value) {
+    if (!pl) return fail("null plan");
+    if (key == 0) {
+        if (value < 0 || value > 2) return fail("gs_pipe must be 0, 1 or 2");
+        pl->gs_pipe = value;
+        return 0;
+    }
+    // key 1 ("chain") is a property of the plan's buffer layout: it can only be chosen at creation (PDEOP_CHAIN)
+    if (key == 1) return fail("the chain-solver choice is fixed when the plan is created (environment PDEOP_CHAIN)");
+    return fail("unknown tuning key");
+}
+extern "C" int pdeop_plan_get_tuning(const pdeop_plan* pl, int key, int* value) {
+    if (!pl || !value) return fail("null argument");
+    if (key == 0) { *value = pl->gs_pipe; return 0; }
+    if (key == 1) { *value = pl->use_chain ? 1 : 0; return 0; }
+    return fail("unknown tuning key");
+}
+extern "C" int pdeop_plan_profile_enable(pdeop_plan* pl, int on) {
+    if (!pl) return fail("null plan");
+    ProfState& p = pl->prof;
+    p.on = on != 0;
+    for (auto& r : p.recs) { p.pool.push_back(r.a); p.pool.push_back(r.b); }
+    p.recs.clear();
+    return 0;
+}
+extern "C" int pdeop_plan_profile_collect(pdeop_plan* pl, double* ms, long long* counts, int ncat) {
+    if (!pl) return -1;
+    ProfState& p = pl->prof;
+    for (int i = 0; i < ncat; ++i) { ms[i] = 0.0; counts[i] = 0; }
+    for (auto& r : p.recs) {
+        if (r.cat < ncat) { ms[r.cat] += be_event_elapsed_ms(r.a, r.b); counts[r.cat] += 1; }
+        p.pool.push_back(r.a);
+        p.pool.push_back(r.b);
+    }
+    p.recs.clear();
+    return PC_COUNT;
+}
+
+extern "C" const char* pdeop_last_error(void) { return g_err.c_str(); }
+extern "C" const char* pdeop_backend_name(void) { return be_name(); }
 
 static double* P_T(const pdeop_plan* pl, void* persist, int l) { return (double*)persist + pl->lev[l].off_T; }
 static double* P_coef(const pdeop_plan* pl, void* persist, int l) { return (double*)persist + pl->lev[l].off_coef; }
@@ -361,7 +424,7 @@ static void setup_operator(pdeop_plan* pl, const double* coeffs, const double* c
     const int B = pl->B;
     be_state_reset(st, sc.state);
     {
-        ProfScope ps(PC_SETUP, st);
+        ProfScope ps(pl->prof, PC_SETUP, st);
         be_pack(st, pl->lev[0].dev, B, coeffs, P_coef(pl, persist, 0));
         for (int l = 0; l < pl->n_grid; ++l) {
             const LevelDev& L = pl->lev[l].dev;
@@ -376,8 +439,8 @@ static void setup_operator(pdeop_plan* pl, const double* coeffs, const double* c
         be_zero_dense(st, B, pl->nc, pl->lev[lc].dev.bw, Kd);
         be_dense(st, pl->lev[lc].dev, B, P_T(pl, persist, lc), P_coef(pl, persist, lc), Kd);
     }
-    ProfScope pf(PC_FACTOR, st);
-    be_cholesky(st, B, pl->nc, pl->lev[pl->n_grid - 1].dev.bw, P_Kd(pl, persist, sc), P_Linv(pl, persist), sc.state);
+    ProfScope pf(pl->prof, PC_FACTOR, st);
+    be_cholesky(st, B, pl->nc, pl->lev[pl->n_grid - 1].dev.bw, P_Kd(pl, persist, sc), P_Linv(pl, persist), sc.state, pl->use_chain);
 }
 
 static void vcycle(pdeop_plan* pl, const pdeop_solver_cfg* cfg, void* persist, Scratch& sc, int l, const double* b,
@@ -386,35 +449,33 @@ static void vcycle(pdeop_plan* pl, const pdeop_solver_cfg* cfg, void* persist, S
     const LevelDev& L = pl->lev[l].dev;
     const int* done = &sc.state->done;
     {
-        ProfScope ps(l == 0 ? PC_GS_FINE : PC_GS_COARSE, st);
+        ProfScope ps(pl->prof, l == 0 ? PC_GS_FINE : PC_GS_COARSE, st);
         be_gs(st, L, B, P_T(pl, persist, l), P_coef(pl, persist, l), P_dinv(pl, persist, l), b, x, sc.gs_stash, sc.gs_stash_stride,
-              cfg->gs_pre, done,
-              cfg->gs_variant);
+              cfg->gs_pre, done, cfg->gs_variant, pl->gs_pipe);
     }
     {
-        ProfScope ps(l == 0 ? PC_APPLY_FINE : PC_APPLY_COARSE, st);
+        ProfScope ps(pl->prof, l == 0 ? PC_APPLY_FINE : PC_APPLY_COARSE, st);
         be_apply_k(st, L, B, P_T(pl, persist, l), P_coef(pl, persist, l), x, b, rtmp, 1, done);
     }
     const LevelDev& Lc = pl->lev[l + 1].dev;
     {
-        ProfScope ps(PC_TRANSFER, st);
+        ProfScope ps(pl->prof, PC_TRANSFER, st);
         be_interp(st, L, Lc, B, L.M, rtmp, sc.lb[l + 1], 0, done);
     }
     if (l + 1 == pl->n_grid - 1) {
-        ProfScope ps(PC_COARSE_SOLVE, st);
-        be_chol_solve(st, Lc, B, P_Kd(pl, persist, sc), P_Linv(pl, persist), sc.lb[l + 1], sc.lx[l + 1], sc.cwork, done);
+        ProfScope ps(pl->prof, PC_COARSE_SOLVE, st);
+        be_chol_solve(st, Lc, B, P_Kd(pl, persist, sc), P_Linv(pl, persist), sc.lb[l + 1], sc.lx[l + 1], sc.cwork, done, pl->use_chain);
     } else {
         be_zero(st, sc.lx[l + 1], (size_t)B * Lc.M * Lc.G * sizeof(double));
         vcycle(pl, cfg, persist, sc, l + 1, sc.lb[l + 1], sc.lx[l + 1], sc.lr[l + 1], st);
     }
     {
-        ProfScope ps(PC_TRANSFER, st);
+        ProfScope ps(pl->prof, PC_TRANSFER, st);
         be_interp(st, Lc, L, B, L.M, sc.lx[l + 1], x, 1, done);
     }
-    ProfScope ps(l == 0 ? PC_GS_FINE : PC_GS_COARSE, st);
+    ProfScope ps(pl->prof, l == 0 ? PC_GS_FINE : PC_GS_COARSE, st);
     be_gs(st, L, B, P_T(pl, persist, l), P_coef(pl, persist, l), P_dinv(pl, persist, l), b, x, sc.gs_stash, sc.gs_stash_stride,
-          cfg->gs_post, done,
-          cfg->gs_variant);
+          cfg->gs_post, done, cfg->gs_variant, pl->gs_pipe);
 }
 
 // z = V-cycle(b) from a zero initial guess (multigrid.py:490-498)
@@ -435,17 +496,17 @@ static void fgmres(pdeop_plan* pl, const pdeop_solver_cfg* cfg, void* persist, S
     const int m = cfg->restart;
     const int* done = &sc.state->done;
     {
-        ProfScope ps(PC_KRYLOV, st);
+        ProfScope ps(pl->prof, PC_KRYLOV, st);
         be_fg_begin(st, sc.n0, b, x, sc.state);
     }
     const int ncycles = (cfg->max_iter + m - 1) / m;
     for (int cyc = 0;; ++cyc) {
         {
-            ProfScope ps(PC_APPLY_FINE, st);
+            ProfScope ps(pl->prof, PC_APPLY_FINE, st);
             be_apply_k(st, L0, B, T0, c0, x, b, sc.w, 1, done);
         }
         {
-            ProfScope ps(PC_KRYLOV, st);
+            ProfScope ps(pl->prof, PC_KRYLOV, st);
             be_fg_resnorm(st, sc.n0, sc.w, sc.state, cfg->max_iter, cfg->atol);
             if (cyc == ncycles) break;
             be_fg_first(st, sc.n0, sc.w, sc.V, sc.state);
@@ -454,13 +515,13 @@ static void fgmres(pdeop_plan* pl, const pdeop_solver_cfg* cfg, void* persist, S
             double* zj = sc.Z + (size_t)j * sc.n0;
             vcycle_start(pl, cfg, persist, sc, sc.V + (size_t)j * sc.n0, zj, sc.w, st);
             {
-                ProfScope ps(PC_APPLY_FINE, st);
+                ProfScope ps(pl->prof, PC_APPLY_FINE, st);
                 be_apply_k(st, L0, B, T0, c0, zj, nullptr, sc.w, 0, done);
             }
-            ProfScope ps(PC_KRYLOV, st);
+            ProfScope ps(pl->prof, PC_KRYLOV, st);
             be_fg_cgs(st, sc.n0, j, m, sc.V, sc.w, sc.state);
         }
-        ProfScope ps(PC_KRYLOV, st);
+        ProfScope ps(pl->prof, PC_KRYLOV, st);
         be_fg_update(st, sc.n0, m, sc.Z, x, sc.state);
     }
 }
@@ -474,7 +535,7 @@ static int check_cfg(const pdeop_solver_cfg* cfg) {
 
 extern "C" int pdeop_mg_setup(pdeop_plan* pl, const double* coeffs, const double* const* cv, const double* const* fv,
                               const double* const* bv, void* persist, void* scratch, double* info_out, void* stream) {
-    if (!pl) return fail("null plan");
+    if (check_plan(pl)) return 1;
     Scratch sc = carve(pl, scratch, 1);
     setup_operator(pl, coeffs, cv, fv, bv, persist, sc, stream);
     if (info_out) be_fg_info(stream, sc.state, info_out);
@@ -485,7 +546,7 @@ extern "C" int pdeop_mg_forward(pdeop_plan* pl, const pdeop_solver_cfg* cfg, con
                                 const double* iv_rhs, const double* const* cv, const double* const* fv,
                                 const double* const* bv, void* persist, void* scratch, double* x_out,
                                 double* info_out, void* stream) {
-    if (!pl) return fail("null plan");
+    if (check_plan(pl)) return 1;
     if (pl->n_grid < 2) return fail("multigrid path needs n_grid >= 2");
     if (check_cfg(cfg)) return 1;
     Scratch sc = carve(pl, scratch, cfg->restart);
@@ -504,7 +565,7 @@ static void run_grads(pdeop_plan* pl, void* persist, Scratch& sc, const double* 
     const LevelDev& L0 = pl->lev[0].dev;
     const int B = pl->B;
     double* xw = sc.V;  // Krylov basis no longer needed
-    ProfScope ps(PC_GRADS, st);
+    ProfScope ps(pl->prof, PC_GRADS, st);
     be_pack(st, L0, B, x_api, xw);
     be_zero(st, d_cv, (size_t)B * L0.Ntot * 12 * sizeof(double));
     be_zero(st, d_fv, (size_t)B * L0.Ftot * 4 * sizeof(double));
@@ -517,7 +578,7 @@ extern "C" int pdeop_mg_backward(pdeop_plan* pl, const pdeop_solver_cfg* cfg, co
                                  const double* fv0, const double* bv0, void* persist, void* scratch, const double* x,
                                  const double* grad_x, double* d_coeffs, double* d_rhs, double* d_iv_rhs, double* d_cv,
                                  double* d_fv, double* d_bv, double* info_out, void* stream) {
-    if (!pl) return fail("null plan");
+    if (check_plan(pl)) return 1;
     if (pl->n_grid < 2) return fail("multigrid path needs n_grid >= 2");
     if (check_cfg(cfg)) return 1;
     Scratch sc = carve(pl, scratch, cfg->restart);
@@ -532,7 +593,7 @@ extern "C" int pdeop_mg_backward(pdeop_plan* pl, const pdeop_solver_cfg* cfg, co
 extern "C" int pdeop_dense_forward(pdeop_plan* pl, const double* coeffs, const double* rhs, const double* iv_rhs,
                                    const double* cv0, const double* fv0, const double* bv0, void* persist,
                                    void* scratch, double* x_out, double* info_out, void* stream) {
-    if (!pl) return fail("null plan");
+    if (check_plan(pl)) return 1;
     if (pl->n_grid != 1) return fail("dense path needs a single-level plan");
     Scratch sc = carve(pl, scratch, 1);
     const double* cvp[1] = {cv0};
@@ -540,7 +601,7 @@ extern "C" int pdeop_dense_forward(pdeop_plan* pl, const double* coeffs, const d
     const double* bvp[1] = {bv0};
     setup_operator(pl, coeffs, cvp, fvp, bvp, persist, sc, stream);
     be_atb(stream, pl->lev[0].dev, pl->B, P_coef(pl, persist, 0), rhs, iv_rhs, sc.atb);
-    be_chol_solve(stream, pl->lev[0].dev, pl->B, P_Kd(pl, persist, sc), P_Linv(pl, persist), sc.atb, sc.x, sc.cwork, nullptr);
+    be_chol_solve(stream, pl->lev[0].dev, pl->B, P_Kd(pl, persist, sc), P_Linv(pl, persist), sc.atb, sc.x, sc.cwork, nullptr, pl->use_chain);
     be_unpack(stream, pl->lev[0].dev, pl->B, sc.x, x_out);
     if (info_out) be_fg_info(stream, sc.state, info_out);
     return check_backend();
@@ -550,12 +611,12 @@ extern "C" int pdeop_dense_backward(pdeop_plan* pl, const double* rhs, const dou
                                     const double* bv0, void* persist, void* scratch, const double* x,
                                     const double* grad_x, double* d_coeffs, double* d_rhs, double* d_iv_rhs,
                                     double* d_cv, double* d_fv, double* d_bv, double* info_out, void* stream) {
-    if (!pl) return fail("null plan");
+    if (check_plan(pl)) return 1;
     if (pl->n_grid != 1) return fail("dense path needs a single-level plan");
     Scratch sc = carve(pl, scratch, 1);
     be_state_reset(stream, sc.state);
     be_pack(stream, pl->lev[0].dev, pl->B, grad_x, sc.atb);
-    be_chol_solve(stream, pl->lev[0].dev, pl->B, P_Kd(pl, persist, sc), P_Linv(pl, persist), sc.atb, sc.x, sc.cwork, nullptr);  // dz (:65)
+    be_chol_solve(stream, pl->lev[0].dev, pl->B, P_Kd(pl, persist, sc), P_Linv(pl, persist), sc.atb, sc.x, sc.cwork, nullptr, pl->use_chain);  // dz (:65)
     if (info_out) be_fg_info(stream, sc.state, info_out);
     run_grads(pl, persist, sc, rhs, cv0, fv0, bv0, x, sc.x, d_coeffs, d_rhs, d_iv_rhs, d_cv, d_fv, d_bv, stream);
     return check_backend();
@@ -564,7 +625,7 @@ extern "C" int pdeop_dense_backward(pdeop_plan* pl, const double* rhs, const dou
 extern "C" int pdeop_fgmres(pdeop_plan* pl, const pdeop_solver_cfg* cfg, int back, const double* b, double* x_out,
                             double* info_out, double* hess_out, void* persist, void* scratch, void* stream) {
     (void)back;
-    if (!pl) return fail("null plan");
+    if (check_plan(pl)) return 1;
     if (check_cfg(cfg)) return 1;
     Scratch sc = carve(pl, scratch, cfg->restart);
     be_state_reset(stream, sc.state);
@@ -579,7 +640,7 @@ extern "C" int pdeop_fgmres(pdeop_plan* pl, const pdeop_solver_cfg* cfg, int bac
 extern "C" int pdeop_stage(pdeop_plan* pl, const pdeop_solver_cfg* cfg, int stage, int level, int count,
                            const double* in1, const double* in2, double* out, void* persist, void* scratch,
                            void* stream) {
-    if (!pl) return fail("null plan");
+    if (check_plan(pl)) return 1;
     if (check_cfg(cfg)) return 1;
     if (level < 0 || level >= pl->n_grid) return fail("level out of range");
     Scratch sc = carve(pl, scratch, cfg->restart);
@@ -600,7 +661,7 @@ extern "C" int pdeop_stage(pdeop_plan* pl, const pdeop_solver_cfg* cfg, int stag
             be_pack(stream, L, B, in1, t1);
             be_pack(stream, L, B, in2, t2);
             be_gs(stream, L, B, P_T(pl, persist, level), P_coef(pl, persist, level), P_dinv(pl, persist, level), t1, t2,
-                  sc.gs_stash, sc.gs_stash_stride, count, nullptr, cfg->gs_variant);
+                  sc.gs_stash, sc.gs_stash_stride, count, nullptr, cfg->gs_variant, pl->gs_pipe);
             be_unpack(stream, L, B, t2, out);
             break;
         case PDEOP_STAGE_RESTRICT: {
@@ -629,7 +690,7 @@ extern "C" int pdeop_stage(pdeop_plan* pl, const pdeop_solver_cfg* cfg, int stag
         case PDEOP_STAGE_COARSE_SOLVE:
             if (level != pl->n_grid - 1) return fail("coarse solve runs on the last level");
             be_pack(stream, L, B, in1, t1);
-            be_chol_solve(stream, L, B, P_Kd(pl, persist, sc), P_Linv(pl, persist), t1, t2, sc.cwork, nullptr);
+            be_chol_solve(stream, L, B, P_Kd(pl, persist, sc), P_Linv(pl, persist), t1, t2, sc.cwork, nullptr, pl->use_chain);
             be_unpack(stream, L, B, t2, out);
             break;
         case PDEOP_STAGE_ATB:

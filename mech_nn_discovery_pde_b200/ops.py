@@ -1,14 +1,25 @@
-"""Autograd operators over the C ABI (include/pdeop.h).
+"""Torch custom operators over the C ABI (include/pdeop.h).
 
-``PdePlan`` owns one native plan (index tables of every multigrid level) and the scratch buffer.
-``MGSolveFn`` / ``DenseSolveFn`` are the torch.autograd.Function pair that replaces the reference's
-``QPFunctionFn`` (solver/qp_dual_sparse_multigrid_normal_kkt.py:21-164,
-solver/qp_dual_dense_normal_kkt.py:19-120).  Inputs and outputs are dense tensors in the reference's
-layouts; the native side never sees a sparse tensor.
+``PdePlan`` owns one native plan (index tables of every multigrid level) and its scratch buffer.  The solve is
+registered with ``torch.library`` as
+
+    torch.ops.pdeop.mg_solve / mg_solve_backward          multigrid-preconditioned FGMRES
+    torch.ops.pdeop.dense_solve / dense_solve_backward    dense Cholesky
+
+with fake-tensor implementations and ``register_autograd`` formulas; they replace the reference's
+``QPFunctionFn`` pair (solver/qp_dual_sparse_multigrid_normal_kkt.py:21-164,
+solver/qp_dual_dense_normal_kkt.py:19-120) and its CuPy dependency.  Inputs and outputs are dense tensors in the
+reference's layouts; the per-call operator state the reference stashes on ``ctx`` (:66-76) is the ``persist``
+output tensor, owned by the autograd graph alone.  ``MGSolveFn`` / ``DenseSolveFn`` keep the round-1 call
+signature on top of the ops.
 """
 import ctypes
+import itertools
+import weakref
+from typing import List, Tuple
 
 import torch
+from torch import Tensor
 
 from . import _lib
 from .config import PDEConfig
@@ -38,18 +49,42 @@ def iv_descriptors(init_index_mi_list, dims_list):
     return desc
 
 
+_PLAN_IDS = itertools.count(1)
+_PLANS = weakref.WeakValueDictionary()   # op argument `plan` (an int) -> PdePlan
+
+
+def plan_from_id(plan_id):
+    plan = _PLANS.get(int(plan_id))
+    if plan is None:
+        raise _lib.PdeopError(f"pdeop: plan {plan_id} does not exist (any more)")
+    return plan
+
+
 class PdePlan:
-    def __init__(self, coord_dims, order, batch, n_grid, downsample_first, init_index_mi_list, library=None):
+    def __init__(self, coord_dims, order, batch, n_grid, downsample_first, init_index_mi_list, library=None,
+                 evolution=False, chain=None, gs_pipe=None, device=None):
         self.lib = library if library is not None else _lib.get_library()
         self.coord_dims = tuple(int(v) for v in coord_dims)
         self.d = len(self.coord_dims)
         self.batch = int(batch)
+        self.order = int(order)
         self.n_grid = int(n_grid)
         self.downsample_first = bool(downsample_first)
+        self.evolution = bool(evolution)
         self.dims_list = level_dims(self.coord_dims, self.n_grid, self.downsample_first)
         self.iv_desc = iv_descriptors(init_index_mi_list, self.dims_list)
-        self.handle = self.lib.plan_create(self.coord_dims, order, self.batch, self.n_grid, self.downsample_first,
-                                           self.iv_desc)
+        # the plan's tables live on ONE device: the requested one, else the current one
+        self.device = None
+        if self.lib.backend.startswith("cuda"):
+            self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+            if self.device.type != "cuda":
+                raise _lib.PdeopError(f"pdeop: device {device} is not a CUDA device; this package has no CPU path")
+            if self.device.index is None:
+                self.device = torch.device("cuda", torch.cuda.current_device())
+        with self.device_guard():
+            self.handle = self.lib.plan_create(self.coord_dims, order, self.batch, self.n_grid,
+                                               self.downsample_first, self.iv_desc, evolution=evolution, chain=chain,
+                                               gs_pipe=gs_pipe)
         q = self.lib.query
         self.M = q(self.handle, _lib.Q_M, 0)
         self.G = q(self.handle, _lib.Q_G, 0)
@@ -60,6 +95,15 @@ class PdePlan:
         self.Ftot = [q(self.handle, _lib.Q_FTOT, l) for l in range(self.n_grid)]
         self.persist_bytes = q(self.handle, _lib.Q_PERSIST_BYTES, 0)
         self._scratch = {}
+        self.id = next(_PLAN_IDS)
+        _PLANS[self.id] = self
+
+    def device_guard(self):
+        """Context manager making the plan's device current (the native entry points check it)."""
+        if self.device is None:
+            import contextlib
+            return contextlib.nullcontext()
+        return torch.cuda.device(self.device)
 
     def __del__(self):
         try:
@@ -83,15 +127,36 @@ class PdePlan:
         return torch.empty(self.persist_bytes // 8, dtype=torch.float64, device=device)
 
     def cfg(self, back=False, config=PDEConfig):
-        c = _lib.SolverCfg()
-        c.gs_pre = int(config.mg_gauss_seidel_steps_pre)
-        c.gs_post = int(config.mg_gauss_seidel_steps_post)
-        c.mg_steps = int(config.mg_steps_backward if back else config.mg_steps_forward)
-        c.max_iter = int(config.mg_fgmres_max_iter_backward if back else config.mg_fgmres_max_iter_forward)
-        c.restart = int(config.mg_fgmres_restarts_backward if back else config.mg_fgmres_restarts_forward)
-        c.atol = float(getattr(config, "mg_fgmres_atol", 1e-5))
-        c.gs_variant = int(getattr(config, "gs_variant", 0))
-        return c
+        return _cfg_struct(knobs_of(config, back), float(getattr(config, "mg_fgmres_atol", 1e-5)))
+
+    # ---- per-plan instrumentation and kernel-variant switch (pdeop.h) ----
+    def profile_enable(self, on=True):
+        self.lib.profile_enable(self.handle, on)
+
+    def profile_collect(self):
+        return self.lib.profile_collect(self.handle)
+
+    def set_tuning(self, key, value):
+        self.lib.set_tuning(self.handle, key, value)
+
+    def get_tuning(self, key):
+        return self.lib.get_tuning(self.handle, key)
+
+
+def knobs_of(config, back):
+    """[gs_pre, gs_post, mg_steps, max_iter, restart, gs_variant] from a PDEConfig-like object (config.py:13-29)."""
+    return [int(config.mg_gauss_seidel_steps_pre), int(config.mg_gauss_seidel_steps_post),
+            int(config.mg_steps_backward if back else config.mg_steps_forward),
+            int(config.mg_fgmres_max_iter_backward if back else config.mg_fgmres_max_iter_forward),
+            int(config.mg_fgmres_restarts_backward if back else config.mg_fgmres_restarts_forward),
+            int(getattr(config, "gs_variant", 0))]
+
+
+def _cfg_struct(knobs, atol):
+    c = _lib.SolverCfg()
+    c.gs_pre, c.gs_post, c.mg_steps, c.max_iter, c.restart, c.gs_variant = [int(v) for v in knobs]
+    c.atol = float(atol)
+    return c
 
 
 def _ptr_array(tensors):
@@ -100,27 +165,227 @@ def _ptr_array(tensors):
 
 def _check_inputs(plan, coeffs, rhs, iv_rhs, cv, fv, bv):
     B = plan.batch
-    assert coeffs.shape == (B, plan.G, plan.M), f"coeffs {tuple(coeffs.shape)}"
-    assert rhs.shape == (B, plan.G), f"rhs {tuple(rhs.shape)}"
-    assert iv_rhs.shape == (B, plan.n_init), f"iv_rhs {tuple(iv_rhs.shape)} expected {(B, plan.n_init)}"
-    assert cv.shape == (B, plan.Ntot[0], 2, 6) and fv.shape == (B, plan.Ftot[0], 4) and bv.shape == fv.shape
-    for t in (coeffs, rhs, iv_rhs, cv, fv, bv):
-        assert t.dtype == torch.float64, "pdeop kernels compute in fp64"
+    want = {"coeffs": (coeffs, (B, plan.G, plan.M)), "rhs": (rhs, (B, plan.G)), "iv_rhs": (iv_rhs, (B, plan.n_init)),
+            "cv": (cv, (B, plan.Ntot[0], 2, 6)), "fv": (fv, (B, plan.Ftot[0], 4)), "bv": (bv, (B, plan.Ftot[0], 4))}
+    for name, (t, shape) in want.items():
+        if tuple(t.shape) != shape:
+            raise ValueError(f"pdeop: {name} has shape {tuple(t.shape)}, expected {shape}")
+        if t.dtype != torch.float64:
+            raise ValueError(f"pdeop: {name} is {t.dtype}; the kernels compute in fp64")
+        if plan.device is not None and t.device != plan.device:
+            raise ValueError(f"pdeop: {name} is on {t.device} but the plan lives on {plan.device}")
 
 
-def _raise_if_not_spd(info, config):
-    if getattr(config, "check_factorization", True):
-        bad = int(info[3].item())
-        if bad != 0:
-            raise torch.linalg.LinAlgError(
-                f"pdeop: Cholesky factorisation failed, leading minor of order {bad} is not positive-definite")
+def _raise_if_not_spd(info):
+    bad = int(info[3].item())
+    if bad != 0:
+        raise torch.linalg.LinAlgError(
+            f"pdeop: Cholesky factorisation failed, leading minor of order {bad} is not positive-definite")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# torch.library operators.  `plan` is the integer id of a live PdePlan; `knobs` = knobs_of(config, back).
+# ---------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("pdeop::mg_solve", mutates_args=())
+def mg_solve(coeffs: Tensor, rhs: Tensor, iv_rhs: Tensor, cv: List[Tensor], fv: List[Tensor], bv: List[Tensor],
+             plan: int, knobs: List[int], knobs_bwd: List[int], atol: float,
+             flags: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """x (B,n), persist, info[4] = FGMRES(A^T A, A^T b) with a V-cycle preconditioner
+    (qp_dual_sparse_multigrid_normal_kkt.py:25-79).  cv/fv/bv: line values of every level."""
+    pl = plan_from_id(plan)
+    lib = pl.lib
+    coeffs, rhs, iv_rhs = coeffs.contiguous(), rhs.contiguous(), iv_rhs.contiguous()
+    cv = [t.contiguous() for t in cv]
+    fv = [t.contiguous() for t in fv]
+    bv = [t.contiguous() for t in bv]
+    _check_inputs(pl, coeffs, rhs, iv_rhs, cv[0], fv[0], bv[0])
+    if not (len(cv) == len(fv) == len(bv) == pl.n_grid):
+        raise ValueError("pdeop: one set of line values per multigrid level is required")
+    dev = coeffs.device
+    cfg = _cfg_struct(knobs, atol)
+    scratch = pl.scratch(dev, max(int(knobs[4]), int(knobs_bwd[4])))
+    persist = pl.new_persist(dev)
+    x = torch.empty(pl.batch, pl.n, dtype=torch.float64, device=dev)
+    info = torch.zeros(4, dtype=torch.float64, device=dev)
+    with pl.device_guard():
+        lib.check(lib.dll.pdeop_mg_forward(pl.handle, ctypes.byref(cfg), _lib._ptr(coeffs), _lib._ptr(rhs),
+                                           _lib._ptr(iv_rhs), _ptr_array(cv), _ptr_array(fv), _ptr_array(bv),
+                                           _lib._ptr(persist), _lib._ptr(scratch), _lib._ptr(x), _lib._ptr(info),
+                                           _lib.current_stream_ptr(dev)))
+    return x, persist, info
+
+
+@mg_solve.register_fake
+def _(coeffs, rhs, iv_rhs, cv, fv, bv, plan, knobs, knobs_bwd, atol, flags):
+    pl = plan_from_id(plan)
+    return (coeffs.new_empty(pl.batch, pl.n), coeffs.new_empty(pl.persist_bytes // 8), coeffs.new_empty(4))
+
+
+@torch.library.custom_op("pdeop::mg_solve_backward", mutates_args=())
+def mg_solve_backward(grad_x: Tensor, x: Tensor, rhs: Tensor, cv0: Tensor, fv0: Tensor, bv0: Tensor, persist: Tensor,
+                      plan: int, knobs: List[int], atol: float
+                      ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """(d_coeffs, d_rhs, d_iv_rhs, d_cv, d_fv, d_bv, info) by implicit differentiation: dz = (A^T A)^-1 g with the
+    same operator and preconditioner left in `persist` (qp_dual_sparse_multigrid_normal_kkt.py:81-162)."""
+    pl = plan_from_id(plan)
+    lib = pl.lib
+    dev = x.device
+    grad_x = grad_x.to(torch.float64).contiguous()
+    cfg = _cfg_struct(knobs, atol)
+    scratch = pl.scratch(dev, int(knobs[4]))
+    B = pl.batch
+    d_coeffs = torch.empty(B, pl.G, pl.M, dtype=torch.float64, device=dev)
+    d_rhs = torch.empty(B, pl.G, dtype=torch.float64, device=dev)
+    d_iv = torch.empty(B, pl.n_init, dtype=torch.float64, device=dev)
+    d_cv, d_fv, d_bv = torch.empty_like(cv0), torch.empty_like(fv0), torch.empty_like(bv0)
+    info = torch.zeros(4, dtype=torch.float64, device=dev)
+    with pl.device_guard():
+        lib.check(lib.dll.pdeop_mg_backward(pl.handle, ctypes.byref(cfg), _lib._ptr(rhs), _lib._ptr(cv0),
+                                            _lib._ptr(fv0), _lib._ptr(bv0), _lib._ptr(persist), _lib._ptr(scratch),
+                                            _lib._ptr(x), _lib._ptr(grad_x), _lib._ptr(d_coeffs), _lib._ptr(d_rhs),
+                                            _lib._ptr(d_iv), _lib._ptr(d_cv), _lib._ptr(d_fv), _lib._ptr(d_bv),
+                                            _lib._ptr(info), _lib.current_stream_ptr(dev)))
+    return d_coeffs, d_rhs, d_iv, d_cv, d_fv, d_bv, info
+
+
+@mg_solve_backward.register_fake
+def _(grad_x, x, rhs, cv0, fv0, bv0, persist, plan, knobs, atol):
+    pl = plan_from_id(plan)
+    B = pl.batch
+    return (x.new_empty(B, pl.G, pl.M), x.new_empty(B, pl.G), x.new_empty(B, pl.n_init), torch.empty_like(cv0),
+            torch.empty_like(fv0), torch.empty_like(bv0), x.new_empty(4))
+
+
+@torch.library.custom_op("pdeop::dense_solve", mutates_args=())
+def dense_solve(coeffs: Tensor, rhs: Tensor, iv_rhs: Tensor, cv: Tensor, fv: Tensor, bv: Tensor, plan: int,
+                flags: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """x (B,n), persist, info[4] = (A^T A)^-1 A^T b by dense Cholesky (qp_dual_dense_normal_kkt.py:23-56)."""
+    pl = plan_from_id(plan)
+    lib = pl.lib
+    coeffs, rhs, iv_rhs, cv, fv, bv = [t.contiguous() for t in (coeffs, rhs, iv_rhs, cv, fv, bv)]
+    _check_inputs(pl, coeffs, rhs, iv_rhs, cv, fv, bv)
+    dev = coeffs.device
+    scratch = pl.scratch(dev, 1)
+    persist = pl.new_persist(dev)
+    x = torch.empty(pl.batch, pl.n, dtype=torch.float64, device=dev)
+    info = torch.zeros(4, dtype=torch.float64, device=dev)
+    with pl.device_guard():
+        lib.check(lib.dll.pdeop_dense_forward(pl.handle, _lib._ptr(coeffs), _lib._ptr(rhs), _lib._ptr(iv_rhs),
+                                              _lib._ptr(cv), _lib._ptr(fv), _lib._ptr(bv), _lib._ptr(persist),
+                                              _lib._ptr(scratch), _lib._ptr(x), _lib._ptr(info),
+                                              _lib.current_stream_ptr(dev)))
+    return x, persist, info
+
+
+@dense_solve.register_fake
+def _(coeffs, rhs, iv_rhs, cv, fv, bv, plan, flags):
+    pl = plan_from_id(plan)
+    return (coeffs.new_empty(pl.batch, pl.n), coeffs.new_empty(pl.persist_bytes // 8), coeffs.new_empty(4))
+
+
+@torch.library.custom_op("pdeop::dense_solve_backward", mutates_args=())
+def dense_solve_backward(grad_x: Tensor, x: Tensor, rhs: Tensor, cv: Tensor, fv: Tensor, bv: Tensor, persist: Tensor,
+                         plan: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """Gradients of dense_solve; reuses the factor in `persist` (qp_dual_dense_normal_kkt.py:58-118)."""
+    pl = plan_from_id(plan)
+    lib = pl.lib
+    dev = x.device
+    grad_x = grad_x.to(torch.float64).contiguous()
+    scratch = pl.scratch(dev, 1)
+    B = pl.batch
+    d_coeffs = torch.empty(B, pl.G, pl.M, dtype=torch.float64, device=dev)
+    d_rhs = torch.empty(B, pl.G, dtype=torch.float64, device=dev)
+    d_iv = torch.empty(B, pl.n_init, dtype=torch.float64, device=dev)
+    d_cv, d_fv, d_bv = torch.empty_like(cv), torch.empty_like(fv), torch.empty_like(bv)
+    info = torch.zeros(4, dtype=torch.float64, device=dev)
+    with pl.device_guard():
+        lib.check(lib.dll.pdeop_dense_backward(pl.handle, _lib._ptr(rhs), _lib._ptr(cv), _lib._ptr(fv), _lib._ptr(bv),
+                                               _lib._ptr(persist), _lib._ptr(scratch), _lib._ptr(x),
+                                               _lib._ptr(grad_x), _lib._ptr(d_coeffs), _lib._ptr(d_rhs),
+                                               _lib._ptr(d_iv), _lib._ptr(d_cv), _lib._ptr(d_fv), _lib._ptr(d_bv),
+                                               _lib._ptr(info), _lib.current_stream_ptr(dev)))
+    return d_coeffs, d_rhs, d_iv, d_cv, d_fv, d_bv, info
+
+
+@dense_solve_backward.register_fake
+def _(grad_x, x, rhs, cv, fv, bv, persist, plan):
+    pl = plan_from_id(plan)
+    B = pl.batch
+    return (x.new_empty(B, pl.G, pl.M), x.new_empty(B, pl.G), x.new_empty(B, pl.n_init), torch.empty_like(cv),
+            torch.empty_like(fv), torch.empty_like(bv), x.new_empty(4))
+
+
+# flags: bit 0 = rhs_grad_fp32_quirk (lp_pde_central_diff.py:1634), bit 1 = check_factorization
+FLAG_RHS_FP32, FLAG_CHECK_SPD = 1, 2
+
+# info of the most recent backward of each plan (what the reference logs, :105-107); read by solver_info()
+_LAST_BWD_INFO = {}
+
+
+def _mg_setup_context(ctx, inputs, output):
+    coeffs, rhs, iv_rhs, cv, fv, bv, plan, knobs, knobs_bwd, atol, flags = inputs
+    x, persist, info = output
+    ctx.plan, ctx.knobs_bwd, ctx.atol, ctx.flags, ctx.n_levels = plan, list(knobs_bwd), atol, flags, len(cv)
+    ctx.save_for_backward(rhs, cv[0], fv[0], bv[0], x, persist, info)
+
+
+def _mg_backward(ctx, grad_x, grad_persist, grad_info):
+    rhs, cv0, fv0, bv0, x, persist, info = ctx.saved_tensors
+    if ctx.flags & FLAG_CHECK_SPD:
+        _raise_if_not_spd(info)   # lazily: the forward never synchronises the host (cholesky_ex check, multigrid.py:439)
+    d_coeffs, d_rhs, d_iv, d_cv, d_fv, d_bv, info_b = torch.ops.pdeop.mg_solve_backward(
+        grad_x, x, rhs, cv0, fv0, bv0, persist, ctx.plan, ctx.knobs_bwd, ctx.atol)
+    _LAST_BWD_INFO[ctx.plan] = info_b
+    if ctx.flags & FLAG_RHS_FP32:
+        d_rhs = d_rhs.float().double()
+    none = [None] * (ctx.n_levels - 1)
+    return (d_coeffs, d_rhs, d_iv, [d_cv] + none, [d_fv] + none, [d_bv] + none, None, None, None, None, None)
+
+
+torch.library.register_autograd("pdeop::mg_solve", _mg_backward, setup_context=_mg_setup_context)
+
+
+def _dense_setup_context(ctx, inputs, output):
+    coeffs, rhs, iv_rhs, cv, fv, bv, plan, flags = inputs
+    x, persist, info = output
+    ctx.plan, ctx.flags = plan, flags
+    ctx.save_for_backward(rhs, cv, fv, bv, x, persist, info)
+
+
+def _dense_backward(ctx, grad_x, grad_persist, grad_info):
+    rhs, cv, fv, bv, x, persist, info = ctx.saved_tensors
+    if ctx.flags & FLAG_CHECK_SPD:
+        _raise_if_not_spd(info)
+    d_coeffs, d_rhs, d_iv, d_cv, d_fv, d_bv, info_b = torch.ops.pdeop.dense_solve_backward(
+        grad_x, x, rhs, cv, fv, bv, persist, ctx.plan)
+    _LAST_BWD_INFO[ctx.plan] = info_b
+    if ctx.flags & FLAG_RHS_FP32:
+        d_rhs = d_rhs.float().double()
+    return d_coeffs, d_rhs, d_iv, d_cv, d_fv, d_bv, None, None
+
+
+torch.library.register_autograd("pdeop::dense_solve", _dense_backward, setup_context=_dense_setup_context)
+
+
+def config_flags(config):
+    return ((FLAG_RHS_FP32 if getattr(config, "rhs_grad_fp32_quirk", False) else 0)
+            | (FLAG_CHECK_SPD if getattr(config, "check_factorization", True) else 0))
 
 
 class _Holder:
-    """Per-call state kept for the backward pass (what the reference stashes on ctx,
-    qp_dual_sparse_multigrid_normal_kkt.py:66-76): the operator tables, coarse coefficients and the
-    coarsest Cholesky factor live in ``persist``."""
-    __slots__ = ("plan", "persist", "coarse", "config", "info_fwd", "info_bwd")
+    """What a layer keeps of its most recent call: the plan, the knobs, and the two 4-double info tensors
+    {iters, r_norm, b_norm, chol_info}.  It does NOT own the persist buffer -- the autograd graph does, so the
+    operator state of a call is released with its graph."""
+    __slots__ = ("plan", "coarse", "config", "info_fwd", "__weakref__")
+
+    @property
+    def info_bwd(self):
+        return _LAST_BWD_INFO.get(self.plan.id)
+
+    def check_factorization(self):
+        """Raises torch.linalg.LinAlgError if the forward's Cholesky failed (synchronises)."""
+        if self.info_fwd is not None:
+            _raise_if_not_spd(self.info_fwd)
 
 
 def new_holder(plan, coarse, config):
@@ -128,112 +393,35 @@ def new_holder(plan, coarse, config):
     h.plan = plan
     h.coarse = coarse
     h.config = config
-    h.persist = None
     h.info_fwd = None
-    h.info_bwd = None
+    _LAST_BWD_INFO.pop(plan.id, None)
     return h
 
 
-def _alloc_grads(plan, cv, fv, bv, dev):
-    B = plan.batch
-    d_coeffs = torch.empty(B, plan.G, plan.M, dtype=torch.float64, device=dev)
-    d_rhs = torch.empty(B, plan.G, dtype=torch.float64, device=dev)
-    d_iv = torch.empty(B, plan.n_init, dtype=torch.float64, device=dev)
-    return d_coeffs, d_rhs, d_iv, torch.empty_like(cv), torch.empty_like(fv), torch.empty_like(bv)
+def mg_solve_call(coeffs, rhs, iv_rhs, cv, fv, bv, holder):
+    """x = torch.ops.pdeop.mg_solve(...) for one layer call; records info on the holder."""
+    plan, config = holder.plan, holder.config
+    cvs = [cv] + [t[0] for t in holder.coarse]
+    fvs = [fv] + [t[1] for t in holder.coarse]
+    bvs = [bv] + [t[2] for t in holder.coarse]
+    x, _persist, info = torch.ops.pdeop.mg_solve(coeffs, rhs, iv_rhs, cvs, fvs, bvs, plan.id, knobs_of(config, False),
+                                                 knobs_of(config, True),
+                                                 float(getattr(config, "mg_fgmres_atol", 1e-5)), config_flags(config))
+    holder.info_fwd = info.detach()
+    return x
 
 
-class MGSolveFn(torch.autograd.Function):
-    """x = FGMRES(A^T A, A^T b) with a V-cycle preconditioner; backward by implicit differentiation."""
-
-    @staticmethod
-    def forward(ctx, coeffs, rhs, iv_rhs, cv, fv, bv, holder):
-        plan = holder.plan
-        lib = plan.lib
-        coeffs, rhs, iv_rhs, cv, fv, bv = [t.contiguous() for t in (coeffs, rhs, iv_rhs, cv, fv, bv)]
-        _check_inputs(plan, coeffs, rhs, iv_rhs, cv, fv, bv)
-        dev = coeffs.device
-        cfg = plan.cfg(False, holder.config)
-        scratch = plan.scratch(dev, max(cfg.restart, int(holder.config.mg_fgmres_restarts_backward)))
-        holder.persist = plan.new_persist(dev)
-        cvs = [cv] + [t[0] for t in holder.coarse]
-        fvs = [fv] + [t[1] for t in holder.coarse]
-        bvs = [bv] + [t[2] for t in holder.coarse]
-        x = torch.empty(plan.batch, plan.n, dtype=torch.float64, device=dev)
-        info = torch.zeros(4, dtype=torch.float64, device=dev)
-        lib.check(lib.dll.pdeop_mg_forward(plan.handle, ctypes.byref(cfg), _lib._ptr(coeffs), _lib._ptr(rhs),
-                                           _lib._ptr(iv_rhs), _ptr_array(cvs), _ptr_array(fvs), _ptr_array(bvs),
-                                           _lib._ptr(holder.persist), _lib._ptr(scratch), _lib._ptr(x),
-                                           _lib._ptr(info), _lib.current_stream_ptr(dev)))
-        holder.info_fwd = info
-        _raise_if_not_spd(info, holder.config)
-        ctx.holder = holder
-        ctx.save_for_backward(rhs, cv, fv, bv, x)
-        return x
-
-    @staticmethod
-    def backward(ctx, grad_x):
-        holder = ctx.holder
-        plan = holder.plan
-        lib = plan.lib
-        rhs, cv, fv, bv, x = ctx.saved_tensors
-        dev = x.device
-        grad_x = grad_x.to(torch.float64).contiguous()
-        cfg = plan.cfg(True, holder.config)
-        scratch = plan.scratch(dev, max(cfg.restart, int(holder.config.mg_fgmres_restarts_forward)))
-        d_coeffs, d_rhs, d_iv, d_cv, d_fv, d_bv = _alloc_grads(plan, cv, fv, bv, dev)
-        info = torch.zeros(4, dtype=torch.float64, device=dev)
-        lib.check(lib.dll.pdeop_mg_backward(plan.handle, ctypes.byref(cfg), _lib._ptr(rhs), _lib._ptr(cv),
-                                            _lib._ptr(fv), _lib._ptr(bv), _lib._ptr(holder.persist),
-                                            _lib._ptr(scratch), _lib._ptr(x), _lib._ptr(grad_x), _lib._ptr(d_coeffs),
-                                            _lib._ptr(d_rhs), _lib._ptr(d_iv), _lib._ptr(d_cv), _lib._ptr(d_fv),
-                                            _lib._ptr(d_bv), _lib._ptr(info), _lib.current_stream_ptr(dev)))
-        holder.info_bwd = info
-        if getattr(holder.config, "rhs_grad_fp32_quirk", False):
-            d_rhs = d_rhs.float().double()   # lp_pde_central_diff.py:1634
-        return d_coeffs, d_rhs, d_iv, d_cv, d_fv, d_bv, None
+def dense_solve_call(coeffs, rhs, iv_rhs, cv, fv, bv, holder):
+    x, _persist, info = torch.ops.pdeop.dense_solve(coeffs, rhs, iv_rhs, cv, fv, bv, holder.plan.id,
+                                                    config_flags(holder.config))
+    holder.info_fwd = info.detach()
+    return x
 
 
-class DenseSolveFn(torch.autograd.Function):
-    """x = (A^T A)^-1 A^T b by dense Cholesky; backward reuses the factor (qp_dual_dense_normal_kkt.py:23-118)."""
+class MGSolveFn:
+    """Round-1 call signature: ``MGSolveFn.apply(coeffs, rhs, iv_rhs, cv, fv, bv, holder)``."""
+    apply = staticmethod(mg_solve_call)
 
-    @staticmethod
-    def forward(ctx, coeffs, rhs, iv_rhs, cv, fv, bv, holder):
-        plan = holder.plan
-        lib = plan.lib
-        coeffs, rhs, iv_rhs, cv, fv, bv = [t.contiguous() for t in (coeffs, rhs, iv_rhs, cv, fv, bv)]
-        _check_inputs(plan, coeffs, rhs, iv_rhs, cv, fv, bv)
-        dev = coeffs.device
-        scratch = plan.scratch(dev, 1)
-        holder.persist = plan.new_persist(dev)
-        x = torch.empty(plan.batch, plan.n, dtype=torch.float64, device=dev)
-        info = torch.zeros(4, dtype=torch.float64, device=dev)
-        lib.check(lib.dll.pdeop_dense_forward(plan.handle, _lib._ptr(coeffs), _lib._ptr(rhs), _lib._ptr(iv_rhs),
-                                              _lib._ptr(cv), _lib._ptr(fv), _lib._ptr(bv), _lib._ptr(holder.persist),
-                                              _lib._ptr(scratch), _lib._ptr(x), _lib._ptr(info),
-                                              _lib.current_stream_ptr(dev)))
-        holder.info_fwd = info
-        _raise_if_not_spd(info, holder.config)
-        ctx.holder = holder
-        ctx.save_for_backward(rhs, cv, fv, bv, x)
-        return x
 
-    @staticmethod
-    def backward(ctx, grad_x):
-        holder = ctx.holder
-        plan = holder.plan
-        lib = plan.lib
-        rhs, cv, fv, bv, x = ctx.saved_tensors
-        dev = x.device
-        grad_x = grad_x.to(torch.float64).contiguous()
-        scratch = plan.scratch(dev, 1)
-        d_coeffs, d_rhs, d_iv, d_cv, d_fv, d_bv = _alloc_grads(plan, cv, fv, bv, dev)
-        info = torch.zeros(4, dtype=torch.float64, device=dev)
-        lib.check(lib.dll.pdeop_dense_backward(plan.handle, _lib._ptr(rhs), _lib._ptr(cv), _lib._ptr(fv),
-                                               _lib._ptr(bv), _lib._ptr(holder.persist), _lib._ptr(scratch),
-                                               _lib._ptr(x), _lib._ptr(grad_x), _lib._ptr(d_coeffs), _lib._ptr(d_rhs),
-                                               _lib._ptr(d_iv), _lib._ptr(d_cv), _lib._ptr(d_fv), _lib._ptr(d_bv),
-                                               _lib._ptr(info), _lib.current_stream_ptr(dev)))
-        holder.info_bwd = info
-        if getattr(holder.config, "rhs_grad_fp32_quirk", False):
-            d_rhs = d_rhs.float().double()
-        return d_coeffs, d_rhs, d_iv, d_cv, d_fv, d_bv, None
+class DenseSolveFn:
+    apply = staticmethod(dense_solve_call)

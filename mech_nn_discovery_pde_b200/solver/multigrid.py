@@ -34,7 +34,7 @@ class MultigridSolver:
         if n_grid < 2:
             raise ValueError("MultigridLayer needs n_grid >= 2")
         self.plan = PdePlan(self.coord_dims, order, bs * n_ind_dim, n_grid, downsample_first, init_index_mi_list,
-                            library=_library)
+                            library=_library, evolution=evolution, device=device)
         self.dim_list = list(self.plan.dims_list)
         self.size_list = [int(np.prod(d)) for d in self.dim_list]
         for dims in self.dim_list:
@@ -80,7 +80,7 @@ class MultigridLayer(nn.Module):
         # the reference hard-codes the fp64 multigrid solver whatever solver_dbl says (multigrid.py:569-570)
         self.mg_solver = MultigridSolver(bs, order, n_ind_dim, n_iv, init_index_mi_list, coord_dims, n_iv_steps,
                                          solver_dbl=True, n_grid=n_grid, evolution=evolution,
-                                         downsample_first=downsample_first, device=None, _library=_library)
+                                         downsample_first=downsample_first, device=device, _library=_library)
         self.pde = self.mg_solver.pde_list[0]
         self.pde.plan = self.mg_solver.plan
         self.n_orders = len(self.pde.var_set.mi_list)

@@ -29,7 +29,8 @@ class PDEDenseLayer(nn.Module):
         self.solver_dbl = solver_dbl
         self.evolution = evolution
         self.double_ret = double_ret
-        self.plan = PdePlan(self.coord_dims, order, bs * n_ind_dim, 1, True, init_index_mi_list, library=_library)
+        self.plan = PdePlan(self.coord_dims, order, bs * n_ind_dim, 1, True, init_index_mi_list, library=_library,
+                            device=device)
         # the reference builds the dense layer's constraints with evolution=False whatever is passed
         # (pde_layer_dense.py:72-75)
         self.pde = PDESYSLP(bs * n_ind_dim, self.coord_dims, order, n_iv, init_index_mi_list, self.plan.n_init,
@@ -76,3 +77,13 @@ class PDEDenseLayer(nn.Module):
         u = u.reshape(self.bs, self.n_ind_dim, *u.shape[1:])
         u0 = u[:, :, :, 0]
         return u0, u, eps
+
+    def solver_info(self):
+        """(info_forward, info_backward) of the last call as (0, 0.0) pairs -- the dense path has no Krylov loop; kept
+        so that callers can treat both layers alike.  Raises torch.linalg.LinAlgError if the factorisation failed
+        (cholesky_ex(check_errors=True), qp_dual_dense_normal_kkt.py:39); syncs."""
+        h = self.last_holder
+        if h is None or h.info_fwd is None:
+            return None, None
+        h.check_factorization()
+        return (0, 0.0), (None if h.info_bwd is None else (0, 0.0))

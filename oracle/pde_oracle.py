@@ -619,6 +619,8 @@ def mg_layer(dims, iv_list, coeffs, rhs, iv_rhs, steps_list, n_grid, downsample_
     lam = mg.b0 - np.stack([mg.A0[i] @ x[i] for i in range(B)])      # :62-63
     res = LayerResult(x=x, lam=lam, info_fwd=info)
     if grad_out is not None:
+        if callable(grad_out):          # upstream gradient as a function of the solution (loss = f(x))
+            grad_out = grad_out(x)
         g = np.asarray(grad_out, dtype=np.float64).reshape(-1)
         tb = {} if trace is not None else None
         dz, info_b = fgmres(K0, g, lambda v: v_cycle_start(mg, v, back=True),

@@ -31,8 +31,9 @@ void be_event_destroy(void*) {}
 void be_event_record(void*, stream_t) {}
 float be_event_elapsed_ms(void*, void*) { return 0.f; }
 long long be_launch_count() { return 0; }
-int be_set_tuning(int, int) { return 0; }
-bool be_chain_active(int, int) { return false; }
+int be_current_device() { return -1; }
+int be_default_gs_pipe() { return 2; }
+bool be_default_chain() { return false; }
 
 static inline size_t vstride(const LevelDev& L) { return (size_t)L.M * L.G; }
 static inline size_t tstride(const LevelDev& L) { return (size_t)L.D * kTabEntries * kTabPitch; }
@@ -108,7 +109,7 @@ static void gs_t(const LevelDev& L, int B, const double* T, const double* coef, 
 }
 
 void be_gs(stream_t, const LevelDev& L, int B, const double* T, const double* coef, const double* dinv,
-           const double* b, double* x, double*, size_t, int nsweeps, const int* done, int) {
+           const double* b, double* x, double*, size_t, int nsweeps, const int* done, int, int) {
     if (done && *done) return;
     if (nsweeps <= 0) return;
     if (L.D == 1) gs_t<1>(L, B, T, coef, dinv, b, x, nsweeps);
@@ -137,7 +138,7 @@ void be_dense(stream_t, const LevelDev& L, int B, const double* T, const double*
         }
 }
 
-void be_cholesky(stream_t, int B, int n, int, double* Kd, double*, FgmresState* state) {
+void be_cholesky(stream_t, int B, int n, int, double* Kd, double*, FgmresState* state, bool) {
     for (int ib = 0; ib < B; ++ib) {
         double* A = Kd + (size_t)ib * n * n;
         for (int j = 0; j < n; ++j) {
@@ -159,7 +160,7 @@ void be_cholesky(stream_t, int B, int n, int, double* Kd, double*, FgmresState* 
 }
 
 void be_chol_solve(stream_t, const LevelDev& L, int B, const double* Lf, const double*, const double* rhs, double* out,
-                   double* work, const int* done) {
+                   double* work, const int* done, bool) {
     if (done && *done) return;
     const int n = L.M * L.G;
     for (int ib = 0; ib < B; ++ib) {

@@ -12,7 +12,7 @@ from mech_nn_discovery_pde_b200.ops import PdePlan, _ptr_array
 from mech_nn_discovery_pde_b200.solver.line_values import coarsen_steps, line_values
 from mech_nn_discovery_pde_b200.solver.multigrid import MultigridLayer
 from mech_nn_discovery_pde_b200.solver.pde_layer_dense import PDEDenseLayer
-from oracle.cases import IV_LISTS
+from oracle.cases import IV_LISTS, make_inputs
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -30,13 +30,53 @@ def load_layer_case(name):
     return z, dims, steps
 
 
+def golden_stride(z):
+    """Round-2 fixtures (oracle/make_golden_r2.py, make_golden_port.py) store large outputs as every stride-th entry
+    of the flattened array plus the norm of the full array."""
+    return int(z["stride"]) if "stride" in z.files else 1
+
+
+def rel_sampled(got, z, key):
+    """Relative error of `got` against golden field `key`, honouring the fixture's sampling stride; also checks the
+    full-array norm when the fixture stores it."""
+    g = np.asarray(got, dtype=np.float64).reshape(-1)
+    ref = np.asarray(z[key], dtype=np.float64).reshape(-1)
+    e = rel(g[::golden_stride(z)], ref)
+    if key + "_norm" in z.files:
+        nrm = float(z[key + "_norm"])
+        e = max(e, abs(float(np.linalg.norm(g)) - nrm) / max(nrm, 1e-300))
+    return e
+
+
+def golden_loss_w(z, dims):
+    """Loss weights of a layer fixture: stored, or (sampled fixtures) regenerated from the seed and checked."""
+    if "loss_w" in z.files:
+        return z["loss_w"]
+    inp = make_inputs(dims, int(z["bs"]), z["iv_rhs"].shape[1], int(z["seed"]), uniform=bool(z["uniform"]))
+    assert np.array_equal(inp["coeffs"], z["coeffs"]), "seeded inputs do not reproduce the fixture's"
+    assert abs(np.linalg.norm(inp["loss_w"]) - float(z["loss_w_norm"])) < 1e-12 * float(z["loss_w_norm"])
+    return inp["loss_w"]
+
+
+def seeded_stage_vectors(s):
+    """(v, x0) of a stagesS_* fixture, regenerated as oracle/make_golden_r2.py drew them."""
+    g = torch.Generator().manual_seed(int(s["seed"]))
+    n = int(s["n"])
+    v = torch.randn(n, generator=g, dtype=torch.float64).numpy()
+    x0 = torch.randn(n, generator=g, dtype=torch.float64).numpy()
+    assert np.array_equal(v[:8], s["v_head"]) and np.array_equal(x0[:8], s["x0_head"])
+    assert abs(np.linalg.norm(v) - float(s["v_norm"])) < 1e-12 * float(s["v_norm"])
+    return v, x0
+
+
 class StageRunner:
     """Operator set-up + single multigrid building blocks through pdeop_mg_setup / pdeop_stage."""
 
-    def __init__(self, lib, device, dims, iv_list, B, n_grid, dsf, coeffs, steps, config=PDEConfig):
+    def __init__(self, lib, device, dims, iv_list, B, n_grid, dsf, coeffs, steps, config=PDEConfig, chain=None):
         self.lib = lib
         self.dev = torch.device(device)
-        self.plan = PdePlan(dims, 2, B, n_grid, dsf, iv_list, library=lib)
+        self.plan = PdePlan(dims, 2, B, n_grid, dsf, iv_list, library=lib, chain=chain,
+                            device=self.dev if self.dev.type == "cuda" else None)
         self.B = B
         self.cfg = self.plan.cfg(False, config)
         t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).to(self.dev)
@@ -97,7 +137,7 @@ def run_layer_case(lib, device, name, config=PDEConfig):
     st = [t(s).requires_grad_(True) for s in steps]
     u0, u, eps = layer(coeffs, rhs, ivr, list(st))
     assert eps is None
-    loss = (u * t(z["loss_w"]).reshape(u.shape)).sum()
+    loss = (u * t(golden_loss_w(z, dims)).reshape(u.shape)).sum()
     loss.backward()
     out = dict(u=u.detach().cpu().numpy(), u0=u0.detach().cpu().numpy(), d_coeffs=coeffs.grad.cpu().numpy(),
                d_rhs=rhs.grad.cpu().numpy(), d_iv_rhs=ivr.grad.cpu().numpy(),

@@ -12,7 +12,8 @@ import torch
 from mech_nn_discovery_pde_b200 import _lib
 from oracle import pde_oracle as O
 from oracle.cases import IV_LISTS, make_inputs
-from tests.helpers import GOLDEN, StageRunner, load_layer_case, rel, run_layer_case
+from tests.helpers import (GOLDEN, StageRunner, load_layer_case, rel, rel_sampled, run_layer_case,
+                           seeded_stage_vectors)
 
 pytestmark = pytest.mark.gpu
 
@@ -64,15 +65,22 @@ def test_stages_vs_reference(lib, name):
 
 
 LAYER_CASES = ["dense_1d_24", "dense_2d_8x10", "dense_2d_12x12_sine_uniform", "dense_3d_8x8x8", "mg_2d_16x16_g2",
-               "mg_2d_32x32_g3", "mg_2d_16x32_g2_nodsf", "mg_3d_8x16x16_g2_nodsf", "mg_3d_16x16x16_g2"]
+               "mg_2d_32x32_g3", "mg_2d_16x32_g2_nodsf", "mg_3d_8x16x16_g2_nodsf", "mg_3d_16x16x16_g2",
+               # round 2 (oracle/make_golden_r2.py): Kamani-shaped batch, the 32x32 sine layer (BASELINE config 1),
+               # four-level 2-D, and 3-D three-level downsample_first=False -- the reference's own GL default
+               # (discovery/ginzburg_landau.py:52-57,241-243) and one size up
+               "dense_1d_24_b256", "dense_2d_32x32_sine", "dense_2d_32x32_sine_nonuniform", "mg_2d_64x64_g4",
+               "mg_3d_8x32x32_g3_nodsf", "mg_3d_16x32x32_g3_nodsf"]
 
 
 def _check_layer(z, out):
     dense = str(z["kind"]) == "dense"
     tol_x, tol_g = (1e-8, 2e-7) if dense else (1e-8, 1e-8)
-    assert rel(out["u"], z["u"]) < tol_x
-    assert rel(out["d_coeffs"], z["d_coeffs"]) < tol_g
-    assert rel(out["d_rhs"], z["d_rhs"]) < tol_g
+    if dense and out["u"].size >= 5000:
+        tol_x, tol_g = 5e-8, 1e-6    # 32x32 sine layer, n = 5120: two direct solvers at cond ~1e11
+    assert rel_sampled(out["u"], z, "u") < tol_x
+    assert rel_sampled(out["d_coeffs"], z, "d_coeffs") < tol_g
+    assert rel_sampled(out["d_rhs"], z, "d_rhs") < tol_g
     assert rel(out["d_iv_rhs"], z["d_iv_rhs"]) < tol_g
     for c in range(len(out["d_steps"])):
         assert rel(out["d_steps"][c], z[f"d_steps{c}"]) < max(tol_g, 1e-7)
@@ -87,6 +95,85 @@ def _check_layer(z, out):
 def test_layer_vs_reference(lib, name):
     z, out = run_layer_case(lib, "cuda:0", name)
     _check_layer(z, out)
+
+
+@pytest.mark.parametrize("name", ["mg_3d_8x32x32_g3_nodsf"])
+def test_seeded_stages_vs_reference(lib, name):
+    """Three-level 3-D stages from the unmodified reference (normal matvec, 5 pipelined GS sweeps, V-cycle through
+    two coarse levels, solver/multigrid.py:453-498); inputs regenerated from the seed, outputs sampled."""
+    s = np.load(os.path.join(GOLDEN, f"stagesS_{name}.npz"))
+    z, dims, steps = load_layer_case(name)
+    B = int(z["bs"])
+    iv = IV_LISTS[str(z["iv_name"])]
+    sr = StageRunner(lib, "cuda:0", dims, iv, B, int(z["n_grid"]), bool(z["dsf"]), z["coeffs"], steps)
+    assert int(sr.info[3].item()) == 0
+    v, x0 = seeded_stage_vectors(s)
+    assert rel_sampled(sr.stage(_lib.STAGE_ATB, 0, z["rhs"], z["iv_rhs"]), s, "Atb") < 1e-13
+    assert rel_sampled(sr.stage(_lib.STAGE_APPLY_K, 0, v), s, "Kv") < 1e-13
+    assert rel_sampled(sr.stage(_lib.STAGE_GS, 0, v, x0, count=5), s, "gs5") < 1e-12
+    assert rel_sampled(sr.stage(_lib.STAGE_VCYCLE, 0, v), s, "vcycle") < 1e-9
+
+
+@pytest.mark.parametrize("B", [1, 2])
+def test_benchmarked_config_vs_oracle(lib, B):
+    """bench.py's default workload itself -- Ginzburg-Landau 32x64x64, n_grid=4, downsample_first=False (coarsest
+    level 32x8x8, n = 14336: chain solver, pipelined GS on two levels), the benchmark's synthetic inputs and loss --
+    against fixtures from the pinned oracle port (oracle/make_golden_port.py; ~10 CPU-minutes per instance)."""
+    import bench
+    from mech_nn_discovery_pde_b200 import MultigridLayer
+    z = np.load(os.path.join(GOLDEN, f"port_gl32_b{B}.npz"))
+    wl = bench.WORKLOADS["gl32"]
+    dev = torch.device("cuda:0")
+    layer = MultigridLayer(bs=B, coord_dims=wl["dims"], order=2, n_ind_dim=1, n_iv=1, n_grid=wl["n_grid"],
+                           downsample_first=wl["dsf"], init_index_mi_list=bench.IV_LISTS[wl["iv"]], n_iv_steps=1)
+    inp = bench.synth_inputs(wl, B, int(z["seed"]))
+    n_init = layer.pde.num_added_initial_constraints
+    iv_rhs = 0.5 * torch.randn(B, n_init, generator=inp["gen"], dtype=torch.float64)
+    theta = bench.theta_init(wl, "cpu").detach()
+    coeffs = bench.assemble_coeffs(wl, inp["coeffs_base"], inp["field"], theta)
+    for name, t in (("coeffs", coeffs), ("rhs", inp["rhs"]), ("iv_rhs", iv_rhs)):   # same inputs as the fixture's
+        nrm = float(z[name + "_norm"])
+        assert abs(float(t.norm()) - nrm) < 1e-12 * nrm
+    coeffs = coeffs.to(dev).requires_grad_(True)
+    rhs = inp["rhs"].to(dev).requires_grad_(True)
+    ivr = iv_rhs.to(dev).requires_grad_(True)
+    steps = [s.to(dev).requires_grad_(True) for s in inp["steps"]]
+    u0, u, _ = layer(coeffs, rhs, ivr, list(steps))
+    (u0 * u0).sum().backward()
+    f, b = layer.solver_info()
+    info = z["info"]
+    assert f[0] == int(info[0, 0]) and b[0] == int(info[1, 0])
+    assert abs(f[1] - info[0, 1]) <= 1e-6 * info[0, 1] and abs(b[1] - info[1, 1]) <= 1e-6 * info[1, 1]
+    assert rel_sampled(u.detach().cpu().numpy(), z, "u") < 1e-8
+    assert rel_sampled(coeffs.grad.cpu().numpy(), z, "d_coeffs") < 1e-8
+    assert rel_sampled(rhs.grad.cpu().numpy(), z, "d_rhs") < 1e-8
+    assert rel(ivr.grad.cpu().numpy(), z["d_iv_rhs"]) < 1e-8
+    for c in range(3):
+        assert rel(steps[c].grad.cpu().numpy(), z[f"d_steps{c}"]) < 1e-7
+
+
+def test_coarse_solve_at_benchmark_size(lib):
+    """Coarsest level of the benchmarked configuration (32x8x8, n = 14336, half-bandwidth 1798): the band Cholesky +
+    chain solver must invert the matrix-free operator of that level (K (K^-1 r) = r), several instances."""
+    dims, B, n_grid, dsf = (32, 64, 64), 2, 4, False
+    iv = IV_LISTS["gl"]
+    G = int(np.prod(dims))
+    g = torch.Generator().manual_seed(7)
+    coeffs = torch.zeros(B, G, 7, dtype=torch.float64)
+    coeffs[..., 0] = 0.1 * torch.randn(B, G, generator=g, dtype=torch.float64)
+    coeffs[..., 1] = 1.0
+    coeffs[..., 5] = -1.0
+    coeffs[..., 6] = -1.0
+    steps = [np.full((B, n - 1), h) for n, h in zip(dims, (0.1, 0.3906, 0.3906))]
+    sr = StageRunner(lib, "cuda:0", dims, iv, B, n_grid, dsf, coeffs.numpy(), steps)
+    assert int(sr.info[3].item()) == 0
+    lc = n_grid - 1
+    nc = sr.level_n(lc)
+    assert nc == 14336
+    r = np.random.default_rng(9).standard_normal(B * nc)
+    sol = sr.stage(_lib.STAGE_COARSE_SOLVE, lc, r)
+    back = sr.stage(_lib.STAGE_APPLY_K, lc, sol)
+    assert rel(back, r) < 1e-8
 
 
 def test_layer_vs_oracle_seeded(lib):
@@ -306,12 +393,10 @@ def test_gs_kernel_variants_bit_identical(lib):
         n = B * G * M
         b, x0 = rng.standard_normal(n), rng.standard_normal(n)
         outs = {}
-        try:
-            for mode in (0, 1):
-                lib.set_tuning("gs_pipe", mode)
-                outs[mode] = sr.stage(_lib.STAGE_GS, 0, b, x0, count=5)
-        finally:
-            lib.set_tuning("gs_pipe", 2)
+        for mode in (0, 1):
+            sr.plan.set_tuning("gs_pipe", mode)     # per-plan switch: nothing to restore for other plans
+            outs[mode] = sr.stage(_lib.STAGE_GS, 0, b, x0, count=5)
+        sr.plan.set_tuning("gs_pipe", 2)
         step_kernel = sr.stage(_lib.STAGE_GS, 0, b, x0, count=5, gs_variant=1)
         assert np.array_equal(outs[0], outs[1])
         assert np.array_equal(outs[0], step_kernel)
@@ -334,16 +419,13 @@ def test_chain_solver_matches_block_row_solver(lib, dims):
     coeffs[..., 6] = -1.0
     steps = [np.full((B, n - 1), h) for n, h in zip(dims, (0.1, 0.39, 0.39))]
     sols = {}
-    try:
-        for mode in (1, 0):
-            lib.set_tuning("chain", mode)   # read at operator set-up
-            sr = StageRunner(lib, "cuda:0", dims, iv, B, n_grid, False, coeffs, steps)
-            nc = sr.level_n(1)
-            rhs = np.random.default_rng(5).standard_normal(B * nc)
-            sols[mode] = sr.stage(_lib.STAGE_COARSE_SOLVE, 1, rhs)
-            if mode == 1:
-                res = rhs - sr.stage(_lib.STAGE_APPLY_K, 1, sols[mode])
-                assert np.linalg.norm(res) < 1e-5 * np.linalg.norm(rhs)
-    finally:
-        lib.set_tuning("chain", 1)
+    for mode in (1, 0):
+        sr = StageRunner(lib, "cuda:0", dims, iv, B, n_grid, False, coeffs, steps, chain=bool(mode))   # fixed per plan
+        assert sr.plan.get_tuning("chain") == mode
+        nc = sr.level_n(1)
+        rhs = np.random.default_rng(5).standard_normal(B * nc)
+        sols[mode] = sr.stage(_lib.STAGE_COARSE_SOLVE, 1, rhs)
+        if mode == 1:
+            res = rhs - sr.stage(_lib.STAGE_APPLY_K, 1, sols[mode])
+            assert np.linalg.norm(res) < 1e-5 * np.linalg.norm(rhs)
     assert rel(sols[1], sols[0]) < 1e-10

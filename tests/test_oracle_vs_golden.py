@@ -9,6 +9,7 @@ import torch
 
 from oracle import pde_oracle as O
 from oracle.cases import IV_LISTS
+from tests.helpers import golden_loss_w, rel_sampled, seeded_stage_vectors
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -61,17 +62,25 @@ def _load_layer(path):
     return z, dims, steps
 
 
+# fixtures whose oracle run takes minutes on the build container's CPU: PDEOP_SLOW=1 enables them
+SLOW = {"layer_mg_3d_16x32x32_g3_nodsf.npz"}
+
+
 @pytest.mark.parametrize("path", LAYERS, ids=[os.path.basename(p) for p in LAYERS])
 def test_layer(path):
+    if os.path.basename(path) in SLOW and not os.environ.get("PDEOP_SLOW"):
+        pytest.skip("minutes of CPU; set PDEOP_SLOW=1 (result recorded in profiles/README.md)")
     z, dims, steps = _load_layer(path)
     iv = IV_LISTS[str(z["iv_name"])]
     B = int(z["bs"])
     G = int(np.prod(dims))
     M = 1 + 2 * len(dims)
-    g_out = z["loss_w"].reshape(B, G * M)
+    g_out = golden_loss_w(z, dims).reshape(B, G * M)
     if str(z["kind"]) == "dense":
         res = O.dense_layer(dims, iv, z["coeffs"], z["rhs"], z["iv_rhs"], steps, grad_out=g_out)
         tol_x, tol_g = 1e-8, 2e-7   # cond(AtA)~1e10: two LAPACK-based direct solves agree to ~1e-9
+        if G * M >= 5000:
+            tol_x, tol_g = 5e-8, 1e-6   # 32x32 sine layer (n = 5120): conditioning grows with the grid
     else:
         res = O.mg_layer(dims, iv, z["coeffs"], z["rhs"], z["iv_rhs"], steps, int(z["n_grid"]), bool(z["dsf"]),
                          grad_out=g_out)
@@ -80,13 +89,32 @@ def test_layer(path):
         assert abs(res.info_fwd[1] - info[0, 1]) <= 1e-6 * info[0, 1]
         assert abs(res.info_bwd[1] - info[1, 1]) <= 1e-6 * info[1, 1]
         tol_x, tol_g = 1e-8, 1e-8
-    assert rel(res.x.reshape(B, 1, G, M), z["u"]) < tol_x
-    assert rel(res.d_coeffs, z["d_coeffs"]) < tol_g
-    assert rel(res.d_rhs, z["d_rhs"]) < tol_g
-    assert rel(res.d_rhs, z["d_rhs_fp32quirk"]) < 1e-6      # shipped add_pad buffer is fp32 (lp_...:1634)
+    assert rel_sampled(res.x, z, "u") < tol_x
+    assert rel_sampled(res.d_coeffs, z, "d_coeffs") < tol_g
+    assert rel_sampled(res.d_rhs, z, "d_rhs") < tol_g
+    if "d_rhs_fp32quirk" in z.files:
+        assert rel(res.d_rhs, z["d_rhs_fp32quirk"]) < 1e-6      # shipped add_pad buffer is fp32 (lp_...:1634)
     assert rel(res.d_iv_rhs, z["d_iv_rhs"]) < tol_g
     for c in range(len(dims)):
         assert rel(res.d_steps[c], z[f"d_steps{c}"]) < max(tol_g, 1e-7)
+
+
+STAGES_SEEDED = sorted(glob.glob(os.path.join(GOLDEN, "stagesS_*.npz")))
+
+
+@pytest.mark.parametrize("path", STAGES_SEEDED, ids=[os.path.basename(p) for p in STAGES_SEEDED])
+def test_mg_stages_seeded(path):
+    """Three-level 3-D V-cycle, 5 Gauss-Seidel sweeps and the normal matvec of the reference's own GL default grid
+    (inputs regenerated from the seed, outputs sampled; oracle/make_golden_r2.py:golden_stages_seeded)."""
+    s = np.load(path)
+    z, dims, steps = _load_layer(path.replace("stagesS_", "layer_"))
+    iv = IV_LISTS[str(z["iv_name"])]
+    mg = O.mg_setup(dims, iv, z["coeffs"], z["rhs"], z["iv_rhs"], steps, int(z["n_grid"]), bool(z["dsf"]))
+    v, x0 = seeded_stage_vectors(s)
+    assert rel_sampled(mg.Atb0, s, "Atb") < 1e-13
+    assert rel_sampled(mg.K_list[0] @ v, s, "Kv") < 1e-13
+    assert rel_sampled(O.smooth_gs(mg.L_list[0], mg.U_list[0], v, x0, 5), s, "gs5") < 1e-12
+    assert rel_sampled(O.v_cycle_start(mg, v), s, "vcycle") < 1e-9
 
 
 @pytest.mark.parametrize("path", STAGES, ids=[os.path.basename(p) for p in STAGES])

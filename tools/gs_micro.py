@@ -33,7 +33,7 @@ def call():
     lib.check(lib.dll.pdeop_stage(sr.plan.handle, ctypes.byref(cfg), _lib.STAGE_GS, 0, 5, _lib._ptr(b), _lib._ptr(x), _lib._ptr(out),
                                   _lib._ptr(sr.persist), _lib._ptr(sr.scratch), _lib.current_stream_ptr(dev)))
 call(); torch.cuda.synchronize()
-lib.profile_enable(False)
+sr.plan.profile_enable(False)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(reps): call()
