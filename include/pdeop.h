@@ -150,7 +150,9 @@ int pdeop_plan_profile_collect(pdeop_plan* plan, double* ms_per_category, long l
 long long pdeop_launch_count(void);
 /* Kernel-variant switch of ONE plan, for A/B tests and profiling (no reference counterpart):
  *   key 0 "gs_pipe": 0 unsplit cluster Gauss-Seidel kernel on every level, 1 software-pipelined kernel on every
- *                    level, 2 (default) pipelined kernel on the latency-bound levels only
+ *                    level, 2 (default) staged kernel (cp.async operand staging, all gathers of a point in flight) on
+ *                    the latency-bound 3-D levels, 3 staged kernel wherever it fits, 4 software-pipelined kernel on
+ *                    the latency-bound levels (round-1 default)
  *   key 1 "chain"  : read-only (pdeop_plan_get_tuning); chosen at creation, see pdeop_plan_opts.chain
  * Returns 0, or nonzero with pdeop_last_error(). */
 int pdeop_plan_set_tuning(pdeop_plan* plan, int key, int value);

@@ -568,6 +568,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_gs_pipe(LevelDev L, const double
 #endif
 }
 
+}  // namespace pdeop
+#include "pdeop_gs_fast.cuh"
+namespace pdeop {
+
 // cross-check variant: one launch per step, no intra-kernel synchronisation
 template <int D>
 __global__ void __launch_bounds__(kThreads) k_gs_step(LevelDev L, const double* __restrict__ T,
@@ -687,6 +691,24 @@ static void launch_gs_pipe(cudaLaunchConfig_t& cfg, const LevelDev& L, const dou
     note(cudaLaunchKernelEx(&cfg, kern, L, T, coef, dinv, b, x, stash, stash_stride, nsweeps, done));
 }
 
+// k_gs_fast (pdeop_gs_fast.cuh): returns false when its shared-memory layout does not fit the level
+template <int D, bool SINGLE, bool STAGE = true, int THREADS = 384>
+static bool launch_gs_fast(cudaLaunchConfig_t& cfg, const LevelDev& L, const double* T, const double* coef,
+                           const double* dinv, const double* b, double* x, int nsweeps, const int* done) {
+    cfg.blockDim = dim3(THREADS);
+    int P = L.N[0] > L.N[1] ? L.N[0] : L.N[1];
+    P = P > L.N[2] ? P : L.N[2];
+    const int nrb = (L.S + 8) * L.N[0] + 8;
+    const size_t smem = GsFastSmem<D>::bytes(P, THREADS, nrb, L.S, STAGE);
+    if (smem > (size_t)227 * 1024) return false;
+    auto kern = k_gs_fast<D, THREADS, SINGLE, STAGE>;
+    ensure_dyn_smem((const void*)kern, smem);
+    cfg.dynamicSmemBytes = smem;
+    if (!SINGLE) fit_cluster_wave(cfg, kern, (int)(cfg.gridDim.x / cfg.attrs[0].val.clusterDim.x));
+    note(cudaLaunchKernelEx(&cfg, kern, L, T, coef, dinv, b, x, nsweeps, P, done));
+    return true;
+}
+
 template <int D>
 static void launch_gs_cluster(cudaStream_t s, const LevelDev& L, int B, const double* T, const double* coef,
                               const double* dinv, const double* b, double* x, double* stash, size_t stash_stride,
@@ -749,7 +771,17 @@ static void launch_gs_cluster(cudaStream_t s, const LevelDev& L, int B, const do
         default: launch_gs_pipe<D, 512, 0, SG>(cfg, L, T, coef, dinv, b, x, stash, stash_stride, nsweeps, done); break;    \
     }
     // (2-D grids: the unsplit kernel is faster -- Burgers 256x256, batch 64: 78.1 vs 74.2 solves/s)
-    const bool use_pipe = stash && (gs_pipe == 1 || (gs_pipe == 2 && D == 3 && want <= 3 * csize));
+    // Latency-bound level: the busiest step holds at most 3 points per thread.  gs_pipe: 0 unsplit cluster kernel on
+    // every level; 1 software-pipelined kernel on every level; 2 (default) k_gs_fast (cp.async-staged operands, all
+    // gathers of a point in flight) on the latency-bound 3-D levels, unsplit kernel elsewhere; 3 k_gs_fast on every
+    // level it fits; 4 as 2 with the software-pipelined kernel instead of k_gs_fast (the round-1 default).
+    const bool latency_level = D == 3 && want <= 3 * csize;
+    const bool use_pipe = stash && (gs_pipe == 1 || (gs_pipe == 4 && latency_level));
+    if (!single && (gs_pipe == 3 || (gs_pipe == 2 && latency_level))) {
+        const bool ok = launch_gs_fast<D, false>(cfg, L, T, coef, dinv, b, x, nsweeps, done);
+        if (ok) return;
+        cfg.blockDim = dim3(threads);
+    }
     if (use_pipe) {
         if (single) { PDEOP_GS_PIPE_DISPATCH(true) } else { PDEOP_GS_PIPE_DISPATCH(false) }
     } else if (single) { PDEOP_GS_DISPATCH(true) } else { PDEOP_GS_DISPATCH(false) }

@@ -376,9 +376,10 @@ def test_fgmres_control_flow(lib):
 
 
 def test_gs_kernel_variants_bit_identical(lib):
-    """The three Gauss-Seidel kernels (unsplit cluster kernel, software-pipelined kernel with the split cluster
-    barrier, one launch per hyperplane step) run the same canonical arithmetic: identical bits, on a level with one
-    point per thread and step and on one with several rounds (register + global stash paths of the pipelined kernel)."""
+    """The four Gauss-Seidel kernels (unsplit cluster kernel, software-pipelined kernel with the split cluster
+    barrier, cp.async-staged kernel with shared-memory table records, one launch per hyperplane step) run the same
+    canonical arithmetic: identical bits, on a level with one point per thread and step and on one with several
+    rounds (register + global stash paths of the pipelined kernel); non-uniform steps exercise every table entry."""
     iv = IV_LISTS["gl"]
     for dims, B, n_grid in (((8, 16, 16), 3, 2), ((32, 32, 32), 2, 3)):
         G, M = int(np.prod(dims)), 7
@@ -393,12 +394,13 @@ def test_gs_kernel_variants_bit_identical(lib):
         n = B * G * M
         b, x0 = rng.standard_normal(n), rng.standard_normal(n)
         outs = {}
-        for mode in (0, 1):
+        for mode in (0, 1, 3):   # unsplit cluster kernel, software-pipelined kernel, staged kernel (k_gs_fast)
             sr.plan.set_tuning("gs_pipe", mode)     # per-plan switch: nothing to restore for other plans
             outs[mode] = sr.stage(_lib.STAGE_GS, 0, b, x0, count=5)
         sr.plan.set_tuning("gs_pipe", 2)
         step_kernel = sr.stage(_lib.STAGE_GS, 0, b, x0, count=5, gs_variant=1)
         assert np.array_equal(outs[0], outs[1])
+        assert np.array_equal(outs[0], outs[3])
         assert np.array_equal(outs[0], step_kernel)
 
 
