@@ -126,6 +126,21 @@ def assemble_coeffs(wl, base, field, theta):
     return coeffs
 
 
+def make_builder(wl):
+    """The same assembly as assemble_coeffs through the fused coefficient-builder kernel:
+    returns build(field, theta) -> coeffs (B,G,M); None where the workload's base coefficients vary per point."""
+    from mech_nn_discovery_pde_b200.coeffs import CoeffBuilder
+    d = len(wl["dims"])
+    M = 1 + 2 * d
+    if wl["iv"] == "gl":       # c0 = theta0 * field, c1 = 1, c5 = theta1, c6 = theta2
+        cb = CoeffBuilder(M, 1, [(0,), (1,)], [(0, 1), (1 + d + 1, 0), (1 + d + 2, 0)], const={1: 1.0})
+        return lambda field, theta: cb([field], theta)[0]
+    if wl["iv"] == "burgers":  # c1 = 1, c2 = theta0 * field, c4 = theta1
+        cb = CoeffBuilder(M, 1, [(0,), (1,)], [(2, 1), (4, 0)], const={1: 1.0})
+        return lambda field, theta: cb([field], theta)[0]
+    return None
+
+
 def theta_init(wl, device):
     if wl["iv"] == "gl":
         return torch.tensor([0.1, -1.0, -1.0], dtype=torch.float64, device=device, requires_grad=True)
@@ -254,10 +269,15 @@ def run_ours(args, wl):
                     rhs=host["rhs"].to(dev, non_blocking=True), iv=host["iv"].to(dev, non_blocking=True),
                     steps=[s.to(dev, non_blocking=True) for s in host["steps"]])
 
+    builder = None if args.no_fused_builder else make_builder(wl)
+
     def step(dv):
         if theta.grad is not None:
             theta.grad = None
-        coeffs = assemble_coeffs(wl, dv["base"], dv["field"], theta)
+        if builder is not None:
+            coeffs = builder(dv["field"], theta)
+        else:
+            coeffs = assemble_coeffs(wl, dv["base"], dv["field"], theta)
         u0, u, _ = layer(coeffs, dv["rhs"], dv["iv"], list(dv["steps"]))
         loss = (u0 * u0).sum()          # upstream gradient g = 2 u0
         loss.backward()
@@ -527,6 +547,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU (default: workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=120.0)
+    ap.add_argument("--no-fused-builder", action="store_true",
+                    help="assemble coeffs with PyTorch ops instead of the fused coefficient-builder kernel")
     ap.add_argument("--no-unmodified-reference", action="store_true",
                     help="reference arm: skip the unmodified-reference cross-check (oracle/_ref)")
     args = ap.parse_args()

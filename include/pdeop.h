@@ -158,6 +158,28 @@ long long pdeop_launch_count(void);
 int pdeop_plan_set_tuning(pdeop_plan* plan, int key, int value);
 int pdeop_plan_get_tuning(const pdeop_plan* plan, int key, int* value);
 
+/* ---- callers either side of the solve -------------------------------------------------
+ * f1, fused coefficient builder.  Replaces the basis-functions x learned-parameters assembly in front of the layer
+ * (discovery/ginzburg_landau.py:354-374, discovery/burgers_dparam_viscous.py:261-279, discovery/kamani.py:252-271):
+ *     out[p,o] = c0[o] + sum_{k<NP, pair_out[k]=o} w[k] * prod_{f<F} pw(fields[f][p], expo[t,f], kind[t,f]),  t = pair_term[k]
+ * with p over the npts = B*G grid points, o < M written to coeffs (npts,M) and o = M to rhs (npts).
+ * kind 0: integer power of the signed value, 1: |value|^expo (real exponent, differentiable), 2: factor absent.
+ * pair_out/pair_term/kind/c0 are HOST arrays (NP<=32, NT<=16, F<=3, M<=7); expo (NT*F), w (NP), fields and outputs
+ * are device pointers (`fields`, `d_fields`: host arrays of F device pointers): learned exponents never visit the host.  The backward produces, in one pass, d_w (NP),
+ * d_expo (NT*F, nonzero for kind 1) and d_fields[f] (npts; NULL entries skipped). */
+int pdeop_coeff_forward(long long npts, int M, int F, int NT, int NP, const int* pair_out, const int* pair_term,
+                        const int* kind, const double* expo, const double* c0, const double* const* fields,
+                        const double* w, double* coeffs, double* rhs, void* stream);
+int pdeop_coeff_backward(long long npts, int M, int F, int NT, int NP, const int* pair_out, const int* pair_term,
+                         const int* kind, const double* expo, const double* c0, const double* const* fields,
+                         const double* w, const double* d_coeffs, const double* d_rhs, double* d_w, double* d_expo,
+                         double* const* d_fields, void* stream);
+/* f3, fused data-loss epilogue (discovery/ginzburg_landau.py:486-510): loss[0] = mean |u0 - target|^p (p = 1 or 2)
+ * and grad = d loss / d u0 (may be NULL), one kernel. */
+int pdeop_loss_forward(long long n, const double* u0, const double* target, int p, double* grad, double* loss,
+                       void* stream);
+const char* pdeop_coeff_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,8 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libpdeop.so")
-SOURCES = ["pdeop_cuda.cu", "pdeop_solver.cpp"]
-HEADERS = ["pdeop_common.h", "pdeop_elem.h", "pdeop_backend.h", "pdeop_lstsq.h"]
+SOURCES = ["pdeop_cuda.cu", "pdeop_solver.cpp", "pdeop_coeff.cu"]
+HEADERS = ["pdeop_common.h", "pdeop_elem.h", "pdeop_backend.h", "pdeop_lstsq.h", "pdeop_gs_fast.cuh"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

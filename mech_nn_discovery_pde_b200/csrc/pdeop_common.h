@@ -64,6 +64,11 @@ struct LevelDev {
     // along the outer axis => bw = 4*inner*M + M - 1).  Cholesky creates no fill outside the band.
     const int* band;     // [G]
     int bw;
+    // Total derivative order of the constraint system (lp_pde_central_diff.py:304-315).  Order 1 has no second-
+    // derivative unknowns: it runs on the same (u, u_c, u_cc) layout with every u_cc coupling exactly zero (the
+    // caller passes zero second-order rows) and a unit diagonal on the u_cc channels, so those unknowns stay zero and
+    // the (u, u_c) block is the order-1 normal operator bit for bit.
+    int order;
 };
 
 PDEOP_HD void unpack_coord(int c, int& i0, int& i1, int& i2) {

@@ -1522,8 +1522,115 @@ bool be_default_chain() {
     return on;
 }
 
+// =================================================================================================
+// Small dense systems (the dense layer on short time grids: Kamani ODE, n = 72, thousands of instances;
+// qp_dual_dense_normal_kkt.py:27-66).  The blocked band path above costs ~25 launches of mostly idle tiles per
+// call at this size; here ONE CTA factors one instance in shared memory (right-looking, column by column), and
+// ONE WARP solves one instance: both triangular sweeps walk ROWS of L (forward: dot products, backward: axpy
+// updates), so L is streamed coalesced from global memory exactly once per sweep and needs no staging.
+// =================================================================================================
+constexpr int kSmallN = 96;
+
+__global__ void __launch_bounds__(256) k_chol_small(int n, double* A, FgmresState* st) {
+    extern __shared__ __align__(16) double cs_a[];   // [n][n+1]
+    const int ld = n + 1;
+    double* Ab = A + (size_t)blockIdx.x * n * n;
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < n * n; idx += blockDim.x) {
+        const int i = idx / n, j = idx - i * n;
+        cs_a[i * ld + j] = j <= i ? Ab[idx] : 0.0;
+    }
+    __syncthreads();
+    for (int j = 0; j < n; ++j) {
+        if (tid == 0) {
+            double d = cs_a[j * ld + j];
+            if (!(d > 0.0)) {
+                atomicCAS(&st->chol_info, 0, j + 1);
+                d = 1.0;
+            }
+            cs_a[j * ld + j] = sqrt(d);
+        }
+        __syncthreads();
+        const double rinv = 1.0 / cs_a[j * ld + j];
+        for (int i = j + 1 + tid; i < n; i += blockDim.x) cs_a[i * ld + j] *= rinv;
+        __syncthreads();
+        const int m = n - j - 1;
+        for (int idx = tid; idx < m * m; idx += blockDim.x) {
+            const int r = idx / m, c = idx - r * m;
+            if (c <= r) {
+                const int i = j + 1 + r, k = j + 1 + c;
+                cs_a[i * ld + k] = fma(-cs_a[i * ld + j], cs_a[k * ld + j], cs_a[i * ld + k]);
+            }
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < n * n; idx += blockDim.x) {
+        const int i = idx / n, j = idx - i * n;
+        if (j <= i) Ab[idx] = cs_a[i * ld + j];
+    }
+}
+
+// out = (L L^T)^-1 rhs, one warp per instance; vectors in band ordering.  Lane l holds entries l, l+32, l+64.
+__global__ void __launch_bounds__(256) k_solve_small(int n, int B, const double* __restrict__ Lf,
+                                                     const double* __restrict__ rhs, double* __restrict__ out,
+                                                     const int* done) {
+    if (done && *done) return;
+    const int ib = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (ib >= B) return;
+    const int lane = threadIdx.x & 31;
+    const double* Lb = Lf + (size_t)ib * n * n;
+    constexpr int R = kSmallN / 32;
+    double y[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) y[r] = lane + 32 * r < n ? rhs[(size_t)ib * n + lane + 32 * r] : 0.0;
+    // forward: y_i = (b_i - sum_{k<i} L[i][k] y_k) / L[i][i], row i read contiguously
+    for (int i = 0; i < n; ++i) {
+        const double* row = Lb + (size_t)i * n;
+        double a = 0.0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int k = lane + 32 * r;
+            if (k < i) a = fma(row[k], y[r], a);
+        }
+        a = warp_sum(a);
+        const double dii = row[i];
+        if (lane == (i & 31)) {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (r == (i >> 5)) y[r] = (y[r] - a) / dii;
+        }
+    }
+    // backward: x_i = y_i / L[i][i]; then y_k -= L[i][k] x_i for k < i (row i again)
+    for (int i = n - 1; i >= 0; --i) {
+        const double* row = Lb + (size_t)i * n;
+        const double dii = row[i];
+        double xi = 0.0;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (r == (i >> 5)) xi = y[r];
+        xi = __shfl_sync(0xffffffffu, xi, i & 31) / dii;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int k = lane + 32 * r;
+            if (k < i) y[r] = fma(-row[k], xi, y[r]);
+            else if (k == i) y[r] = xi;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+        if (lane + 32 * r < n) out[(size_t)ib * n + lane + 32 * r] = y[r];
+}
+
 void be_cholesky(stream_t st, int B, int n, int bw, double* Kd, double* Linv, FgmresState* state, bool use_chain) {
     cudaStream_t s = (cudaStream_t)st;
+    if (n <= kSmallN) {
+        const size_t smem = (size_t)n * (n + 1) * sizeof(double);
+        ensure_dyn_smem((const void*)k_chol_small, smem);
+        k_chol_small<<<B, 256, smem, s>>>(n, Kd, state);
+        PDEOP_COUNT(1);
+        PDEOP_LAUNCH_CHECK();
+        return;
+    }
     const size_t strideA = (size_t)n * n;
     for (int K0 = 0; K0 < n; K0 += kOuter) {
         const int K1 = K0 + kOuter < n ? K0 + kOuter : n;
@@ -2117,6 +2224,13 @@ void be_chol_solve(stream_t st, const LevelDev& L, int B, const double* Lf, cons
     double* y = work + (size_t)B * n;   // solution in band ordering
     k_to_band<<<dim3(cdiv(L.G, kThreads), B), kThreads, 0, s>>>(L, rhs, rb, done);
     PDEOP_COUNT(1);
+    if (n <= kSmallN) {   // one warp per instance (k_chol_small left the factor in Lf)
+        k_solve_small<<<cdiv(B, 8), 256, 0, s>>>(n, B, Lf, rb, y, done);
+        k_from_band<<<dim3(cdiv(L.G, kThreads), B), kThreads, 0, s>>>(L, y, out, done);
+        PDEOP_COUNT(2);
+        PDEOP_LAUNCH_CHECK();
+        return;
+    }
     const ChainLayout cl = be_chain_layout(n, bw);
     if (cl.use && use_chain) {
         // L^-1 = Wt^-1 D^-1, L^-T = D^-T Wt^-T: block-diagonal product, two chains, block-diagonal product

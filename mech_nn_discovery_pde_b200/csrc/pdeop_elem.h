@@ -150,6 +150,7 @@ PDEOP_HD void build_table_elem(const LevelDev& L, int a, int ip, const double* c
             t[T_UU + 5] += g[0] * g[3];
         }
     }
+    if (L.order == 1 && i >= 0 && i < n) t[T_QQ] += 1.0;   // decoupled unit diagonal on the unused u_cc channel
     for (int e = 0; e < kTabEntries; ++e) Ta[(size_t)e * kTabPitch + ip] = t[e];
 }
 

@@ -107,6 +107,7 @@ static int build_level(pdeop_plan* pl, LevelHost& lh, const int* dims, int n_iv,
     for (int a = 0; a < 3; ++a)
         if (L.N[a] > 1023) return fail("grid extent above 1023 not supported");
     L.D = D;
+    L.order = pl->order;
     L.M = 1 + 2 * D;
     L.G = L.N[0] * L.N[1] * L.N[2];
     L.S = L.N[0] + L.N[1] + L.N[2] - 2;
@@ -163,7 +164,7 @@ static int build_level(pdeop_plan* pl, LevelHost& lh, const int* dims, int n_iv,
     for (int k = 0; k < n_iv; ++k) {
         const int* dsc = iv_desc + (size_t)k * (1 + 2 * D);
         int mi = dsc[0];
-        if (mi < 0 || mi >= L.M) return fail("initial-condition multi-index out of range");
+        if (mi < 0 || mi >= 1 + pl->order * D) return fail("initial-condition multi-index out of range");
         int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
         for (int c = 0; c < D; ++c) {
             lo[3 - D + c] = std::max(0, dsc[1 + c]);
@@ -217,9 +218,10 @@ extern "C" int pdeop_plan_create_ex(int d, const int* dims, int order, int batch
     if (!out) return fail("null out");
     *out = nullptr;
     if (d < 1 || d > 3) return fail("dimension must be 1, 2 or 3");
-    if (order != 2) return fail("only total order 2 is implemented");
+    if (order != 1 && order != 2) return fail("total order must be 1 or 2");
     if (batch < 1 || n_grid < 1) return fail("batch and n_grid must be positive");
     if (batch > 65535) return fail("batch above 65535 not supported (instances map to gridDim.y)");
+    if (opts && opts->evolution) return fail("evolution=True equation rows are not implemented");
     pdeop_plan* pl = new pdeop_plan();
     pl->device = be_current_device();
     pl->gs_pipe = (opts && opts->gs_pipe >= 0) ? opts->gs_pipe : be_default_gs_pipe();

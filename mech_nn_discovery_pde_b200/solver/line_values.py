@@ -27,8 +27,8 @@ def _fd_weights(nodes):
     return torch.linalg.solve(vander, target.expand(*vander.shape[:-2], 5, 2))
 
 
-def central_line_values(steps):
-    """steps (B, n-1) -> (B, n, 2, 6).
+def central_line_values(steps, order=2):
+    """steps (B, n-1) -> (B, n, order, 6).
 
     Positions 0,1 and n-2,n-1 use one-sided 5-point stencils, the rest centred ones
     (lp_pde_central_diff.py:1000-1006).  The reference builds the one-sided node sets from
@@ -61,30 +61,44 @@ def central_line_values(steps):
     w = torch.cat([w_left, w_mid, w_right], dim=1)           # (B, n, 5, 2)
     h = torch.cat([h_left, h_mid, h_right], dim=1).unsqueeze(-1)  # (B, n, 1)
     rows = []
-    for k in (1, 2):
+    for k in range(1, order + 1):
         hk = h ** k
         rows.append(torch.cat([w[..., k - 1] * hk, -hk], dim=-1))   # (:1349-1350, :1429-1430)
     return torch.stack(rows, dim=2)
 
 
-def forward_line_values(steps):
-    """(B, n-1) -> (B, n-1, 4) = [1, h, h^2/2, -1]  (lp_pde_central_diff.py:785-848, 1550-1581)."""
+def forward_line_values(steps, order=2):
+    """(B, n-1) -> (B, n-1, order+2) = [1, h, (h^2/2,) -1]  (lp_pde_central_diff.py:785-848, 1550-1581)."""
     one = torch.ones_like(steps)
-    return torch.stack([one, steps, steps * steps / 2.0, -one], dim=-1)
+    mid = [steps] if order == 1 else [steps, steps * steps / 2.0]
+    return torch.stack([one] + mid + [-one], dim=-1)
 
 
-def backward_line_values(steps):
-    """(B, n-1) -> (B, n-1, 4) = [1, -h, h^2/2, -1]; entry i belongs to line position i+1 (:849-861, 1583-1615)."""
+def backward_line_values(steps, order=2):
+    """(B, n-1) -> (B, n-1, order+2) = [1, -h, (h^2/2,) -1]; entry i belongs to line position i+1 (:849-861, 1583-1615)."""
     one = torch.ones_like(steps)
-    return torch.stack([one, -steps, steps * steps / 2.0, -one], dim=-1)
+    mid = [-steps] if order == 1 else [-steps, steps * steps / 2.0]
+    return torch.stack([one] + mid + [-one], dim=-1)
 
 
-def line_values(steps_list):
-    """[(B, n_c-1)]_c -> cv (B, Ntot, 2, 6), fv (B, Ftot, 4), bv (B, Ftot, 4), coordinate-major."""
-    cv = torch.cat([central_line_values(s) for s in steps_list], dim=1).contiguous()
-    fv = torch.cat([forward_line_values(s) for s in steps_list], dim=1).contiguous()
-    bv = torch.cat([backward_line_values(s) for s in steps_list], dim=1).contiguous()
+def line_values(steps_list, order=2):
+    """[(B, n_c-1)]_c -> cv (B, Ntot, order, 6), fv (B, Ftot, order+2), bv (B, Ftot, order+2), coordinate-major."""
+    cv = torch.cat([central_line_values(s, order) for s in steps_list], dim=1).contiguous()
+    fv = torch.cat([forward_line_values(s, order) for s in steps_list], dim=1).contiguous()
+    bv = torch.cat([backward_line_values(s, order) for s in steps_list], dim=1).contiguous()
     return cv, fv, bv
+
+
+def embed_order(cv, fv, bv):
+    """Line values of a total-order-1 system in the kernels' order-2 shapes: a zero second-derivative central row and
+    a zero u_cc entry in the forward/backward rows (the native plan then keeps the u_cc unknowns decoupled)."""
+    if cv.shape[2] == 2:
+        return cv, fv, bv
+    cv2 = torch.cat([cv, torch.zeros_like(cv)], dim=2)
+    z = torch.zeros_like(fv[..., :1])
+    fv2 = torch.cat([fv[..., :2], z, fv[..., 2:]], dim=-1)
+    bv2 = torch.cat([bv[..., :2], z, bv[..., 2:]], dim=-1)
+    return cv2.contiguous(), fv2.contiguous(), bv2.contiguous()
 
 
 def coarsen_steps(steps_list, dims, downsample_first):

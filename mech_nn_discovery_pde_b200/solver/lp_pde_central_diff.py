@@ -58,6 +58,21 @@ class QPVariableSet:
         return grid_pointer * self.n_vars_per_step + int(index[1])
 
 
+class SparseValues(torch.autograd.Function):
+    """values of a (possibly uncoalesced) sparse COO tensor in construction order; the gradient is a sparse tensor on
+    the same pattern (what the reference's backward returns for dA / dD, qp_dual_sparse_multigrid_normal_kkt.py:132-162)."""
+
+    @staticmethod
+    def forward(ctx, sp):
+        ctx.idx = sp._indices()
+        ctx.shape = sp.shape
+        return sp._values().clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return torch.sparse_coo_tensor(ctx.idx, g, ctx.shape, check_invariants=False)
+
+
 class PDESYSLP:
     """Closed-form counts of the constraint system A = [equation; initial; derivative] rows
     (lp_pde_central_diff.py:1063-1139).  Row counts:
@@ -131,15 +146,141 @@ class PDESYSLP:
         out.index_copy_(1, g, eq_values)
         return out.reshape(eq_values.shape[0], *self.coord_dims)
 
-    def build_equation_tensor(self, coeffs):
+    def build_equation_tensor(self, coeffs, sparse=False):
         """Values of the equation rows, (B, n_eq, M), in the reference's value order (row-major over equation
-        rows, then multi-index; :1707-1719).  Dense carrier instead of torch.sparse_coo_tensor."""
-        return self.remove_pad(coeffs, coeffs=True)
+        rows, then multi-index; :1707-1719).  Default: dense carrier.  sparse=True: the reference's own return type,
+        a torch.sparse_coo_tensor (B, n_eq, n) whose values are these numbers in construction order."""
+        vals = self.remove_pad(coeffs, coeffs=True)
+        if not sparse:
+            return vals
+        idx = self.equation_indices(vals.device)
+        return torch.sparse_coo_tensor(idx, vals.reshape(-1), (self.bs, self.num_added_equation_constraints,
+                                                               self.var_set.num_vars), dtype=vals.dtype,
+                                       check_invariants=False)
 
-    def build_derivative_tensor(self, steps_list):
+    def build_derivative_tensor(self, steps_list, sparse=False):
         """Values of the derivative rows per line position: (central (B,Ntot,2,6), forward (B,Ftot,4), backward
-        (B,Ftot,4)) -- build_derivative_values (:1618-1630) before its expansion over the grid."""
-        return line_values(steps_list)
+        (B,Ftot,4)) -- build_derivative_values (:1618-1630) before its expansion over the grid.  sparse=True: the
+        reference's return type, torch.sparse_coo_tensor (B, n_deriv, n) holding the expanded per-nonzero values in
+        construction order [central | forward | backward] (:1721-1731)."""
+        cv, fv, bv = line_values(steps_list, self.order)
+        if not sparse:
+            return cv, fv, bv
+        rows, cols, src = self.derivative_structure(cv.device)
+        B = cv.shape[0]
+        flat = torch.cat([cv.reshape(B, -1), fv.reshape(B, -1), bv.reshape(B, -1)], dim=1)
+        vals = flat.index_select(1, src)                          # expansion over the other grid directions
+        nnz = rows.numel()
+        bidx = torch.arange(B, device=cv.device).repeat_interleave(nnz)
+        idx = torch.stack([bidx, rows.repeat(B), cols.repeat(B)])
+        return torch.sparse_coo_tensor(idx, vals.reshape(-1), (B, self.num_added_derivative_constraints,
+                                                               self.var_set.num_vars), dtype=vals.dtype,
+                                       check_invariants=False)
+
+    # ---- sparse-tensor adapter (the reference's QPFunction takes torch.sparse tensors,
+    # ---- qp_dual_sparse_multigrid_normal_kkt.py:25-33): closed-form COO structure in construction order -----------
+    def equation_indices(self, device=None):
+        """(3, B*n_eq*M) [batch, row, col] of the equation block: row r = r-th interior point in C order, columns
+        g*M + m (lp_pde_central_diff.py:746-764, 1171-1190)."""
+        if getattr(self, "_eq_idx", None) is None:
+            g = self.equation_grid_pointers()
+            M = self.var_set.n_vars_per_step
+            n_eq = g.numel()
+            rows = torch.arange(n_eq).repeat_interleave(M)
+            cols = (g.cpu()[:, None] * M + torch.arange(M)[None, :]).reshape(-1)
+            b = torch.arange(self.bs).repeat_interleave(n_eq * M)
+            self._eq_idx = torch.stack([b, rows.repeat(self.bs), cols.repeat(self.bs)])
+        if device is not None and self._eq_idx.device != device:
+            self._eq_idx = self._eq_idx.to(device)
+        return self._eq_idx
+
+    def derivative_structure(self, device=None):
+        """(rows, cols, src) of the derivative block's nonzeros in construction order: central rows coordinate-major,
+        grid C order, derivative order ascending, 5 stencil columns + the own derivative channel (:886-1006); forward
+        rows [u, u_c, u_cc, u(next)] over the points off the far edge, backward rows [u, u_c, u_cc, u(prev)] over
+        the points off the near edge (:785-884).  src maps each nonzero to its entry of the flattened line values
+        [central (Ntot,order,6) | forward (Ftot,order+2) | backward (Ftot,order+2)]."""
+        if getattr(self, "_d_struct", None) is None:
+            dims, d, order = self.coord_dims, self.n_coord, self.order
+            M = self.var_set.n_vars_per_step
+            G = self.var_set.grid_size
+            idx = np.indices(dims).reshape(d, G)
+            gptr = np.arange(G)
+            strides = np.array([int(np.prod(dims[c + 1:])) for c in range(d)], dtype=np.int64)
+            chan = lambda c, k: 1 + c if k == 1 else 1 + d + c
+            ks = list(range(1, order + 1))
+            tc = order + 2
+            rows, cols, src = [], [], []
+            r0 = 0
+            cvoff = np.concatenate([[0], np.cumsum(dims)])[:-1]
+            fvoff = np.concatenate([[0], np.cumsum([n - 1 for n in dims])])[:-1]
+            n_cv = int(sum(dims)) * order * 6
+            n_fv = int(sum(n - 1 for n in dims)) * tc
+            for c in range(d):
+                i = idx[c]
+                nc = dims[c]
+                off = np.tile(np.arange(5) - 2, (G, 1))
+                off[i <= 1] = np.arange(5)
+                off[(i > 1) & (i >= nc - 2)] = -np.arange(5)
+                ucols = (gptr[:, None] + off * strides[c]) * M
+                for kk, k in enumerate(ks):
+                    own = gptr * M + chan(c, k)
+                    cc = np.concatenate([ucols, own[:, None]], axis=1)                     # (G, 6)
+                    rr = r0 + gptr * order + kk
+                    ss = ((cvoff[c] + i)[:, None] * order + kk) * 6 + np.arange(6)[None, :]
+                    rows.append((np.repeat(rr, 6), kk))
+                    cols.append(cc.reshape(-1))
+                    src.append(ss.reshape(-1))
+                # interleave the per-order blocks so that entries follow (grid point, order) as constructed
+                r_k = [rows[-order + j][0].reshape(G, 6) for j in range(order)]
+                c_k = [cols[-order + j].reshape(G, 6) for j in range(order)]
+                s_k = [src[-order + j].reshape(G, 6) for j in range(order)]
+                del rows[-order:], cols[-order:], src[-order:]
+                rows.append((np.stack(r_k, axis=1).reshape(-1), 0))
+                cols.append(np.stack(c_k, axis=1).reshape(-1))
+                src.append(np.stack(s_k, axis=1).reshape(-1))
+                r0 += G * order
+            rows = [r[0] for r in rows]
+            for c in range(d):      # forward
+                sel = gptr[idx[c] != dims[c] - 1]
+                ent = [sel * M] + [sel * M + chan(c, k) for k in ks] + [(sel + strides[c]) * M]
+                rows.append(np.repeat(r0 + np.arange(sel.shape[0]), tc))
+                cols.append(np.stack(ent, axis=1).reshape(-1))
+                src.append((n_cv + (fvoff[c] + idx[c][sel])[:, None] * tc + np.arange(tc)[None, :]).reshape(-1))
+                r0 += sel.shape[0]
+            for c in range(d):      # backward: line value i belongs to line position i + 1
+                sel = gptr[idx[c] != 0]
+                ent = [sel * M] + [sel * M + chan(c, k) for k in ks] + [(sel - strides[c]) * M]
+                rows.append(np.repeat(r0 + np.arange(sel.shape[0]), tc))
+                cols.append(np.stack(ent, axis=1).reshape(-1))
+                src.append((n_cv + n_fv + (fvoff[c] + idx[c][sel] - 1)[:, None] * tc
+                            + np.arange(tc)[None, :]).reshape(-1))
+                r0 += sel.shape[0]
+            assert r0 == self.num_added_derivative_constraints
+            self._d_struct = tuple(torch.as_tensor(np.concatenate(a), dtype=torch.long) for a in (rows, cols, src))
+        if device is not None and self._d_struct[0].device != device:
+            self._d_struct = tuple(t.to(device) for t in self._d_struct)
+        return self._d_struct
+
+    def line_values_from_sparse(self, derivative_constraints):
+        """Inverse of build_derivative_tensor(sparse=True): per-line values (cv, fv, bv) from the per-nonzero values
+        of a derivative-constraint sparse tensor in construction order (one representative nonzero per line value);
+        differentiable, so the gradient comes back as a sparse tensor on the same pattern."""
+        rows, cols, src = self.derivative_structure(derivative_constraints.device)
+        B = self.bs
+        vals = SparseValues.apply(derivative_constraints).reshape(B, -1)
+        n_line = int(src.max().item()) + 1
+        rep = torch.full((n_line,), -1, dtype=torch.long, device=vals.device)
+        pos = torch.arange(src.numel() - 1, -1, -1, device=vals.device)
+        rep[src.flip(0)] = pos                       # first occurrence wins
+        flat = vals.index_select(1, rep)
+        d, order = self.n_coord, self.order
+        ncv = sum(self.coord_dims) * order * 6
+        nfv = sum(n - 1 for n in self.coord_dims) * (order + 2)
+        cv = flat[:, :ncv].reshape(B, -1, order, 6)
+        fv = flat[:, ncv:ncv + nfv].reshape(B, -1, order + 2)
+        bv = flat[:, ncv + nfv:].reshape(B, -1, order + 2)
+        return cv.contiguous(), fv.contiguous(), bv.contiguous()
 
     def get_solution_reshaped(self, x):
         """(B, n) -> (B, G, M)  (lp_pde_central_diff.py:486-494)."""

@@ -8,7 +8,7 @@ import torch.nn as nn
 from ..config import PDEConfig
 from ..ops import PdePlan
 from . import qp_dual_sparse_multigrid_normal_kkt as MGS
-from .line_values import coarsen_steps, line_values
+from .line_values import coarsen_steps, embed_order, line_values
 from .lp_pde_central_diff import PDESYSLP
 
 
@@ -52,7 +52,7 @@ class MultigridSolver:
         cur = [s.detach() for s in steps_list]
         for l in range(1, self.n_grid):
             cur = coarsen_steps(cur, self.dim_list[l - 1], self.downsample_first)
-            out.append(line_values(cur))
+            out.append(embed_order(*line_values(cur, self.order)))
         return out
 
 
@@ -118,8 +118,9 @@ class MultigridLayer(nn.Module):
         steps = [s.double() for s in steps_list]
 
         # same call sequence as the reference (multigrid.py:607-611)
-        derivative_constraints = self.pde.build_derivative_tensor(steps)
-        eq_constraints = self.pde.build_equation_tensor(coeffs)
+        sparse = getattr(self, "sparse_constraints", False)   # True: torch.sparse tensors, as the reference passes
+        derivative_constraints = self.pde.build_derivative_tensor(steps, sparse=sparse)
+        eq_constraints = self.pde.build_equation_tensor(coeffs, sparse=sparse)
         x = self.qpf(eq_constraints, rhs, iv_rhs, derivative_constraints, coeffs, steps)
         eps = None
         u = self.pde.get_solution_reshaped(x)

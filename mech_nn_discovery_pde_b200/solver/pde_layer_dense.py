@@ -69,8 +69,9 @@ class PDEDenseLayer(nn.Module):
         steps = [s.double() for s in steps_list]
 
         # same call sequence as the reference (pde_layer_dense.py:107-110)
-        derivative_constraints = self.pde.build_derivative_tensor(steps)
-        eq_constraints = self.pde.build_equation_tensor(coeffs)
+        sparse = getattr(self, "sparse_constraints", False)   # True: torch.sparse tensors, as the reference passes
+        derivative_constraints = self.pde.build_derivative_tensor(steps, sparse=sparse)
+        eq_constraints = self.pde.build_equation_tensor(coeffs, sparse=sparse)
         x = self.qpf(eq_constraints, rhs, iv_rhs, derivative_constraints, coeffs, steps)
         eps = None
         u = self.pde.get_solution_reshaped(x)

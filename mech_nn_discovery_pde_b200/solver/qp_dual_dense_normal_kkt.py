@@ -3,6 +3,8 @@ the B200-native dense path.  Same callable signature and gradient routing as the
 import torch
 
 from ..config import PDEConfig
+from .line_values import embed_order
+from .lp_pde_central_diff import SparseValues
 from ..ops import DenseSolveFn, new_holder
 
 
@@ -10,11 +12,20 @@ def QPFunction(pde, double_ret=True, config=PDEConfig):
     def fn(eq_constraints, rhs, iv_rhs, derivative_constraints, coeffs, steps_list):
         B, G, M = pde.bs, pde.var_set.grid_size, pde.var_set.n_vars_per_step
         g = pde.equation_grid_pointers(rhs.device)
+        if eq_constraints.is_sparse:            # the reference's own argument type (:25-33): values in construction order
+            eq_constraints = SparseValues.apply(eq_constraints).reshape(B, -1, M)
+        if torch.is_tensor(derivative_constraints):
+            derivative_constraints = pde.line_values_from_sparse(derivative_constraints)
         full = coeffs.detach().reshape(B, G, M).to(torch.float64).index_copy(1, g, eq_constraints.to(torch.float64))
-        cv, fv, bv = derivative_constraints
+        cv, fv, bv = embed_order(*derivative_constraints)
+        plan = pde.plan
+        if full.shape[-1] < plan.M:      # total order 1: the kernels' (u, u_c, u_cc) layout with zero u_cc columns
+            full = torch.cat([full, full.new_zeros(B, G, plan.M - M)], dim=-1)
         holder = new_holder(pde.plan, [], fn.config)
         x = DenseSolveFn.apply(full, rhs, iv_rhs, cv, fv, bv, holder)
         fn.last_holder = holder
+        if M < plan.M:
+            x = x.reshape(B, G, plan.M)[..., :M].reshape(B, G * M)
         return x
 
     fn.config = config

@@ -116,8 +116,9 @@ class StageRunner:
         return out.cpu().numpy()
 
 
-def run_layer_case(lib, device, name, config=PDEConfig):
-    """Forward + backward of the product layer on a golden case; returns dict of numpy results."""
+def run_layer_case(lib, device, name, config=PDEConfig, sparse=False):
+    """Forward + backward of the product layer on a golden case; returns dict of numpy results.
+    sparse=True: the layer hands torch.sparse constraint tensors to its QPFunction, as the reference does."""
     z, dims, steps = load_layer_case(name)
     iv = IV_LISTS[str(z["iv_name"])]
     B = int(z["bs"])
@@ -131,6 +132,7 @@ def run_layer_case(lib, device, name, config=PDEConfig):
                                evolution=False, downsample_first=bool(z["dsf"]), init_index_mi_list=iv, n_iv_steps=1,
                                double_ret=True, solver_dbl=True, _library=lib)
     layer.config = config
+    layer.sparse_constraints = sparse
     coeffs = t(z["coeffs"]).requires_grad_(True)
     rhs = t(z["rhs"]).requires_grad_(True)
     ivr = t(z["iv_rhs"]).requires_grad_(True)

@@ -47,6 +47,22 @@ LAYER_CASES = ["dense_1d_24", "dense_2d_8x10", "dense_2d_12x12_sine_uniform", "m
                "mg_2d_16x32_g2_nodsf"]
 
 
+@pytest.mark.parametrize("name", ["dense_2d_8x10", "mg_2d_16x16_g2"])
+def test_sparse_tensor_adapter(name):
+    """QPFunction fed with torch.sparse constraint tensors (the reference's argument types,
+    qp_dual_sparse_multigrid_normal_kkt.py:25-33): same solution and the same gradients w.r.t. coeffs / rhs / iv_rhs /
+    steps as the dense-carrier path and the reference."""
+    lib = emu_library()
+    z, out = run_layer_case(lib, "cpu", name, sparse=True)
+    z2, ref = run_layer_case(lib, "cpu", name, sparse=False)
+    assert rel(out["u"], ref["u"]) < 1e-14
+    assert rel(out["d_coeffs"], ref["d_coeffs"]) < 1e-13
+    assert rel(out["d_rhs"], ref["d_rhs"]) < 1e-13
+    for c in range(len(out["d_steps"])):
+        assert rel(out["d_steps"][c], ref["d_steps"][c]) < 1e-12
+        assert rel(out["d_steps"][c], z[f"d_steps{c}"]) < 1e-6
+
+
 @pytest.mark.parametrize("name", LAYER_CASES)
 def test_layer_vs_reference(name):
     lib = emu_library()
@@ -216,3 +232,52 @@ def check_fgmres_control_flow(lib, device):
 
 def test_fgmres_control_flow():
     check_fgmres_control_flow(emu_library(), "cpu")
+
+
+SURFACE_CASES = ["dense_2d_8x10_order1", "mg_2d_16x16_order1", "dense_1d_24_nind3"]
+
+
+def run_surface_case(lib, device, name):
+    """Total order 1 and n_ind_dim > 1 through the layer surface, against the unmodified reference
+    (oracle/make_golden_surface.py; lp_pde_central_diff.py:304-315, pde_layer_dense.py:83-125)."""
+    import os
+    import torch
+    from oracle.cases import IV_LISTS
+    from tests.helpers import GOLDEN
+    from mech_nn_discovery_pde_b200 import MultigridLayer, PDEDenseLayer
+    z = np.load(os.path.join(GOLDEN, f"surf_{name}.npz"))
+    dims = tuple(int(v) for v in z["dims"])
+    bs, n_ind, order = int(z["bs"]), int(z["n_ind"]), int(z["order"])
+    iv = IV_LISTS[str(z["iv_name"])]
+    dev = torch.device(device)
+    kw = dict(bs=bs, coord_dims=dims, order=order, n_ind_dim=n_ind, n_iv=1, init_index_mi_list=iv, n_iv_steps=1,
+              double_ret=True, solver_dbl=True, _library=lib)
+    if str(z["kind"]) == "dense":
+        layer = PDEDenseLayer(**kw)
+    else:
+        layer = MultigridLayer(n_grid=int(z["n_grid"]), downsample_first=True, **kw)
+    G = int(np.prod(dims))
+    M = layer.n_orders
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).to(dev)
+    coeffs = t(z["coeffs"]).reshape(bs, n_ind, G, M).requires_grad_(True)
+    rhs = t(z["rhs"]).reshape(bs, n_ind, G).requires_grad_(True)
+    ivr = t(z["iv_rhs"]).reshape(bs, n_ind, -1).requires_grad_(True)
+    steps = [t(z[f"steps{c}"]).reshape(bs, n_ind, -1).requires_grad_(True) for c in range(len(dims))]
+    u0, u, eps = layer(coeffs, rhs, ivr, list(steps))
+    assert tuple(u.shape) == tuple(z["u"].shape) and tuple(u0.shape) == tuple(z["u0"].shape)
+    (u * t(z["loss_w"]).reshape(u.shape)).sum().backward()
+    tol_g = 2e-7 if str(z["kind"]) == "dense" else 1e-8
+    assert rel(u.detach().cpu().numpy(), z["u"]) < 1e-8
+    assert rel(coeffs.grad.cpu().numpy(), z["d_coeffs"]) < tol_g
+    assert rel(rhs.grad.cpu().numpy(), z["d_rhs"]) < tol_g
+    assert rel(ivr.grad.cpu().numpy(), z["d_iv_rhs"]) < tol_g
+    for c in range(len(dims)):
+        assert rel(steps[c].grad.cpu().numpy(), z[f"d_steps{c}"]) < 1e-7
+    if "info" in z.files:
+        f, _ = layer.solver_info()
+        assert f[0] == int(z["info"][0, 0])
+
+
+@pytest.mark.parametrize("name", SURFACE_CASES)
+def test_surface_order1_and_n_ind_dim(name):
+    run_surface_case(emu_library(), "cpu", name)

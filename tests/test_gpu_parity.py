@@ -431,3 +431,81 @@ def test_chain_solver_matches_block_row_solver(lib, dims):
             res = rhs - sr.stage(_lib.STAGE_APPLY_K, 1, sols[mode])
             assert np.linalg.norm(res) < 1e-5 * np.linalg.norm(rhs)
     assert rel(sols[1], sols[0]) < 1e-10
+
+
+@pytest.mark.parametrize("name", ["dense_2d_8x10_order1", "mg_2d_16x16_order1", "dense_1d_24_nind3"])
+def test_surface_order1_and_n_ind_dim(lib, name):
+    """Total order 1 (dense and multigrid) and n_ind_dim > 1 against the unmodified reference."""
+    from tests.test_emu_structure import run_surface_case
+    run_surface_case(lib, "cuda:0", name)
+
+
+@pytest.mark.parametrize("name", ["dense_2d_8x10", "mg_2d_16x16_g2", "mg_3d_8x16x16_g2_nodsf"])
+def test_sparse_tensor_adapter(lib, name):
+    """QPFunction fed with torch.sparse constraint tensors, the reference's argument types
+    (qp_dual_sparse_multigrid_normal_kkt.py:25-33): same results as the dense carriers and as the reference."""
+    z, out = run_layer_case(lib, "cuda:0", name, sparse=True)
+    _check_layer(z, out)
+
+
+def test_interleaved_graphs_on_one_layer(lib):
+    """forward(A), forward(B), backward(A), backward(B) on ONE layer: each graph owns its operator state (persist),
+    so the gradients equal those of separate runs (the factor of A must not be overwritten by B)."""
+    from mech_nn_discovery_pde_b200 import MultigridLayer
+    dims, B = (8, 16, 16), 2
+    iv = IV_LISTS["gl"]
+    dev = torch.device("cuda:0")
+    layer = MultigridLayer(bs=B, coord_dims=dims, order=2, n_ind_dim=1, n_iv=1, n_grid=2, downsample_first=False,
+                           init_index_mi_list=iv, n_iv_steps=1)
+    n_init = layer.pde.num_added_initial_constraints
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
+    cases = []
+    for seed in (1, 2):
+        inp = make_inputs(dims, B, n_init, seed=seed)
+        cases.append([t(inp["coeffs"]).requires_grad_(True), t(inp["rhs"]), t(inp["iv_rhs"]),
+                      [t(s) for s in inp["steps"]], t(inp["loss_w"])])
+    def separate(c):
+        co = c[0].detach().clone().requires_grad_(True)
+        u0, u, _ = layer(co, c[1], c[2], list(c[3]))
+        (u * c[4].reshape(u.shape)).sum().backward()
+        return co.grad.clone()
+    want = [separate(c) for c in cases]
+    outs = [layer(c[0], c[1], c[2], list(c[3]))[1] for c in cases]       # forward A, forward B
+    for c, u in zip(cases, outs):                                         # backward A, backward B
+        (u * c[4].reshape(u.shape)).sum().backward()
+    for c, w in zip(cases, want):
+        assert torch.equal(c[0].grad, w)
+
+
+def test_two_devices_one_process(lib):
+    """Plans on two GPUs in one process (per-device caches, device recorded in the plan)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from mech_nn_discovery_pde_b200 import MultigridLayer
+    dims, B = (16, 16), 2
+    iv = IV_LISTS["burgers"]
+    res = []
+    for d in (0, 1):
+        dev = torch.device("cuda", d)
+        layer = MultigridLayer(bs=B, coord_dims=dims, order=2, n_ind_dim=1, n_iv=1, n_grid=2, downsample_first=True,
+                               init_index_mi_list=iv, n_iv_steps=1, device=dev)
+        inp = make_inputs(dims, B, layer.pde.num_added_initial_constraints, seed=5)
+        t = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
+        u0, u, _ = layer(t(inp["coeffs"]), t(inp["rhs"]), t(inp["iv_rhs"]), [t(s) for s in inp["steps"]])
+        res.append(u.cpu())
+    assert torch.equal(res[0], res[1])
+
+
+def test_wrong_device_is_an_error(lib):
+    """A plan used while another device is current fails with a message, not an illegal address."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import ctypes
+    sr_dims = (16, 16)
+    coeffs = np.zeros((1, 256, 5)); coeffs[..., 1] = 1.0
+    steps = [np.full((1, 15), 0.1), np.full((1, 15), 0.1)]
+    sr = StageRunner(lib, "cuda:0", sr_dims, IV_LISTS["burgers"], 1, 2, True, coeffs, steps)
+    with torch.cuda.device(1):
+        cfg = sr.plan.cfg(False)
+        rc = lib.dll.pdeop_stage(sr.plan.handle, ctypes.byref(cfg), _lib.STAGE_APPLY_K, 0, 0, None, None, None, None, None, None)
+        assert rc != 0 and b"device" in lib.dll.pdeop_last_error()
