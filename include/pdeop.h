@@ -123,6 +123,34 @@ int pdeop_dense_backward(pdeop_plan* plan, const double* rhs, const double* cv0,
                          double* d_coeffs, double* d_rhs, double* d_iv_rhs, double* d_cv, double* d_fv,
                          double* d_bv, double* info_out, void* stream);
 
+/* ---- converged mode -----------------------------------------------------------
+ * The reference's live solver stops at its iteration cap far from convergence.  This mode
+ * solves the same normal equations A^T A x = A^T b to a per-instance RELATIVE tolerance: preconditioned conjugate
+ * gradients with per-instance dot products, step lengths and convergence masks (the semantics of
+ * solver/cg.py:51-147 cg_matvec: converged instances stop moving, non-finite alpha/beta are zeroed), preconditioned
+ * by one SYMMETRIC V-cycle: polynomial smoother on D^-1 K -- weighted Jacobi (solver/multigrid.py:407-416
+ * smooth_jacobi, weight clamped to 1.8 / lambda_max) or Chebyshev over [1.1 lambda_max/cheb_ratio, 1.1 lambda_max] with
+ * lambda_max(D^-1 K) estimated per instance and level by power iteration --, restriction by the transpose of the
+ * linear prolongation, rediscretised coarse operators, dense Cholesky on the coarsest level.
+ * info_out: {iterations, max_b ||r_b||/||b_b||, 0, chol_info}. */
+typedef struct pdeop_pcg_cfg {
+    int max_iter;      /* PCG iteration cap */
+    double rtol;       /* per-instance relative residual tolerance */
+    int smoother;      /* 0 weighted Jacobi, 1 Chebyshev */
+    int sweeps;        /* smoother steps (Jacobi) / polynomial degree (Chebyshev), each side of the coarse correction */
+    double jacobi_w;   /* config.jacobi_w (config.py:29) */
+    int power_iters;   /* power-iteration steps for lambda_max(D^-1 K) */
+    double cheb_ratio; /* Chebyshev smoothing interval [1.1 lambda_max / cheb_ratio, 1.1 lambda_max]; 30 if <= 1 */
+} pdeop_pcg_cfg;
+int pdeop_mg_forward_converged(pdeop_plan* plan, const pdeop_pcg_cfg* cfg, const double* coeffs, const double* rhs,
+                               const double* iv_rhs, const double* const* cv, const double* const* fv,
+                               const double* const* bv, void* persist, void* scratch, double* x_out, double* info_out,
+                               void* stream);
+int pdeop_mg_backward_converged(pdeop_plan* plan, const pdeop_pcg_cfg* cfg, const double* rhs, const double* cv0,
+                                const double* fv0, const double* bv0, void* persist, void* scratch, const double* x,
+                                const double* grad_x, double* d_coeffs, double* d_rhs, double* d_iv_rhs, double* d_cv,
+                                double* d_fv, double* d_bv, double* info_out, void* stream);
+
 /* Operator set-up only (levels' tables, coarse coefficients, coarsest factor): the part of
  * QPFunctionFn.forward before the Krylov solve.  Needed before pdeop_stage. */
 int pdeop_mg_setup(pdeop_plan* plan, const double* coeffs, const double* const* cv, const double* const* fv,

@@ -27,6 +27,12 @@ class PlanOpts(ctypes.Structure):
     _fields_ = [("evolution", c_int), ("chain", c_int), ("gs_pipe", c_int), ("reserved", c_int * 5)]
 
 
+class PcgCfg(ctypes.Structure):
+    """pdeop_pcg_cfg: converged-mode knobs."""
+    _fields_ = [("max_iter", c_int), ("rtol", ctypes.c_double), ("smoother", c_int), ("sweeps", c_int),
+                ("jacobi_w", ctypes.c_double), ("power_iters", c_int), ("cheb_ratio", ctypes.c_double)]
+
+
 class SolverCfg(ctypes.Structure):
     _fields_ = [("gs_pre", c_int), ("gs_post", c_int), ("mg_steps", c_int), ("max_iter", c_int),
                 ("restart", c_int), ("atol", ctypes.c_double), ("gs_variant", c_int)]
@@ -36,7 +42,8 @@ EXPORTS = [
     "pdeop_plan_create", "pdeop_plan_destroy", "pdeop_plan_query", "pdeop_last_error", "pdeop_backend_name",
     "pdeop_mg_forward", "pdeop_mg_backward", "pdeop_dense_forward", "pdeop_dense_backward", "pdeop_mg_setup",
     "pdeop_stage", "pdeop_fgmres", "pdeop_plan_profile_enable", "pdeop_plan_profile_collect", "pdeop_launch_count",
-    "pdeop_plan_set_tuning", "pdeop_plan_get_tuning", "pdeop_plan_create_ex",
+    "pdeop_plan_set_tuning", "pdeop_plan_get_tuning", "pdeop_plan_create_ex", "pdeop_mg_forward_converged",
+    "pdeop_mg_backward_converged",
 ]
 
 TUNING_KEYS = {"gs_pipe": 0, "chain": 1}
@@ -82,6 +89,9 @@ class PdeopLibrary:
         CFG = ctypes.POINTER(SolverCfg)
         d.pdeop_mg_forward.argtypes = [c_void_p, CFG] + [c_void_p] * 3 + [PP] * 3 + [c_void_p] * 5
         d.pdeop_mg_backward.argtypes = [c_void_p, CFG] + [c_void_p] * 16
+        PCG = ctypes.POINTER(PcgCfg)
+        d.pdeop_mg_forward_converged.argtypes = [c_void_p, PCG] + [c_void_p] * 3 + [PP] * 3 + [c_void_p] * 5
+        d.pdeop_mg_backward_converged.argtypes = [c_void_p, PCG] + [c_void_p] * 16
         d.pdeop_dense_forward.argtypes = [c_void_p] + [c_void_p] * 11
         d.pdeop_dense_backward.argtypes = [c_void_p] + [c_void_p] * 16
         d.pdeop_mg_setup.argtypes = [c_void_p, c_void_p] + [PP] * 3 + [c_void_p] * 4

@@ -31,3 +31,16 @@ class PDEConfig:
     check_factorization = True
     # 0: production wavefront Gauss-Seidel kernel; 1: one launch per hyperplane (debug cross-check)
     gs_variant = 0
+
+    # --- converged mode (north-star subsystems (b)/(c)) --------------------
+    # "reference": the reference's live algorithm -- FGMRES(10) capped at 40 iterations with a Gauss-Seidel V-cycle, the
+    #   batch sharing one Krylov space (iterate parity with the reference, usually far from converged);
+    # "converged": per-instance PCG to a relative tolerance with a symmetric V-cycle (polynomial smoother, R = P^T),
+    #   validated against the exact least-squares solution (solver/cg.py:51-147 semantics).
+    solver_mode = "reference"
+    mg_pcg_rtol = 1e-8
+    mg_pcg_max_iter = 1000
+    mg_smoother = "chebyshev"      # or "jacobi" (weighted Jacobi with jacobi_w, solver/multigrid.py:407-416)
+    mg_smoother_sweeps = 8
+    mg_power_iters = 12
+    mg_cheb_ratio = 30.0           # Chebyshev smoothing interval [1.1 lambda_max / ratio, 1.1 lambda_max]

@@ -100,6 +100,32 @@ void be_grads(stream_t st, const LevelDev& L, int B, const double* coef, const d
               const double* fv, const double* bv, const double* x, const double* dz, double* d_coeffs,
               double* d_rhs, double* d_iv, double* d_cv, double* d_fv, double* d_bv);
 
+// ---- converged mode: per-instance PCG with a symmetric V-cycle (cg.py:51-147 semantics) ----
+// All vectors are (B, n) contiguous; s_* are device arrays of B doubles.
+// out[b] (+)= sum_i a[b,i] * c[b,i]   (out must be zeroed by the caller: be_zero)
+void be_bdot(stream_t st, size_t n, int B, const double* a, const double* c, double* out, const int* done);
+// alpha_b = active_b ? rz_b / pAp_b (0 when not finite) : 0;  x += alpha p;  r -= alpha Ap;  rr[b] += sum r^2
+void be_pcg_xr(stream_t st, size_t n, int B, double* x, double* r, const double* p, const double* Ap, const double* rz,
+               const double* pAp, const double* active, double* rr, const int* done);
+// beta_b = active_b ? rz_new_b / rz_b (0 when not finite) : 0;  p = z + beta p
+void be_pcg_p(stream_t st, size_t n, int B, double* p, const double* z, const double* rz_new, const double* rz,
+              const double* active, const int* done);
+// per-instance bookkeeping after an iteration: active_b &= (sqrt(rr_b) > rtol * bnorm_b); rz = rz_new; zero rz_new,
+// pAp, rr; iters += 1; relres = max_b sqrt(rr_b)/bnorm_b; done = no instance active.  first != 0: initialise (active_b =
+// bnorm_b > 0, iters = 0) from bb[b] = ||b_b||^2 stored in rr
+void be_pcg_scalars(stream_t st, int B, double* active, double* rz, double* rz_new, double* pAp, double* rr,
+                    double* bnorm, double rtol, FgmresState* state, int first);
+// polynomial smoother step: d = c1 d + w_b * dinv .* r;  x += d, with w_b = c2 (mode 0), c2 / lam[b] (mode 1:
+// Chebyshev coefficients are in units of lambda_max) or min(c2, 1.8 / lam[b]) (mode 2: weighted Jacobi kept convergent)
+void be_poly_update(stream_t st, size_t n, int B, double* x, double* d, const double* r, const double* dinv, double c1,
+                    double c2, const double* lam, int mode, const int* done);
+void be_copy(stream_t st, void* dst, const void* src, size_t bytes);
+// restriction by the TRANSPOSE of the linear prolongation (full-weighting-like, R = P^T): out (coarse) = P^T in (fine)
+void be_restrict_t(stream_t st, const LevelDev& Lf, const LevelDev& Lc, int B, int C, const double* in, double* out,
+                   const int* done);
+// power iteration step for lambda_max(D^-1 K): v <- dinv .* Kv / ||dinv .* Kv||_b,  lam[b] = ||dinv .* Kv||_b (||v||_b = 1)
+void be_power_step(stream_t st, size_t n, int B, double* v, const double* Kv, const double* dinv, double* lam, double* tmpB);
+
 // FGMRES vector steps on flat vectors of length n (whole local batch: global norms, fgmres.py:76,128,158)
 void be_fg_begin(stream_t st, size_t n, const double* b, double* x, FgmresState* s);
 void be_fg_resnorm(stream_t st, size_t n, const double* r, FgmresState* s, int maxiter, double atol);

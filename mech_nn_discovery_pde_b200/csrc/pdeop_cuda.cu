@@ -1019,6 +1019,200 @@ static void launch_dots(cudaStream_t s, size_t n, const double* V, size_t ldv, i
     PDEOP_LAUNCH_CHECK();
 }
 
+// =================================================================================================
+// Converged mode: per-instance PCG vector kernels, polynomial smoother update, transpose restriction
+// =================================================================================================
+__global__ void __launch_bounds__(kThreads) k_bdot(size_t n, const double* __restrict__ a, const double* __restrict__ c,
+                                                   double* out, const int* done) {
+    if (done && *done) return;
+    __shared__ double sm[8];
+    const size_t o = (size_t)blockIdx.y * n;
+    double acc = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        acc = fma(a[o + i], c[o + i], acc);
+    const double r = block_sum(acc, sm);
+    if (threadIdx.x == 0) atomicAdd(out + blockIdx.y, r);
+}
+static inline unsigned bvec_blocks(size_t n, int B) {
+    size_t want = (n + (size_t)kThreads * 4 - 1) / ((size_t)kThreads * 4);
+    const size_t cap = (size_t)(4 * 148 + B - 1) / B;   // ~4 CTAs per SM over the whole batch
+    if (want > cap) want = cap;
+    return (unsigned)(want < 1 ? 1 : want);
+}
+void be_bdot(stream_t st, size_t n, int B, const double* a, const double* c, double* out, const int* done) {
+    k_bdot<<<dim3(bvec_blocks(n, B), B), kThreads, 0, (cudaStream_t)st>>>(n, a, c, out, done);
+    PDEOP_COUNT(1);
+    PDEOP_LAUNCH_CHECK();
+}
+
+__device__ __forceinline__ double safe_ratio(double a, double b) {
+    const double q = a / b;
+    return isfinite(q) ? q : 0.0;   // cg.py:112,125 nan_to_num
+}
+
+__global__ void __launch_bounds__(kThreads) k_pcg_xr(size_t n, double* __restrict__ x, double* __restrict__ r,
+                                                     const double* __restrict__ p, const double* __restrict__ Ap,
+                                                     const double* rz, const double* pAp, const double* active,
+                                                     double* rr, const int* done) {
+    if (done && *done) return;
+    __shared__ double sm[8];
+    const int b = blockIdx.y;
+    const double alpha = active[b] != 0.0 ? safe_ratio(rz[b], pAp[b]) : 0.0;
+    const size_t o = (size_t)b * n;
+    double acc = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        x[o + i] = fma(alpha, p[o + i], x[o + i]);
+        const double rn = fma(-alpha, Ap[o + i], r[o + i]);
+        r[o + i] = rn;
+        acc = fma(rn, rn, acc);
+    }
+    const double s = block_sum(acc, sm);
+    if (threadIdx.x == 0) atomicAdd(rr + b, s);
+}
+void be_pcg_xr(stream_t st, size_t n, int B, double* x, double* r, const double* p, const double* Ap, const double* rz,
+               const double* pAp, const double* active, double* rr, const int* done) {
+    k_pcg_xr<<<dim3(bvec_blocks(n, B), B), kThreads, 0, (cudaStream_t)st>>>(n, x, r, p, Ap, rz, pAp, active, rr, done);
+    PDEOP_COUNT(1);
+    PDEOP_LAUNCH_CHECK();
+}
+
+__global__ void __launch_bounds__(kThreads) k_pcg_p(size_t n, double* __restrict__ p, const double* __restrict__ z,
+                                                    const double* rz_new, const double* rz, const double* active,
+                                                    const int* done) {
+    if (done && *done) return;
+    const int b = blockIdx.y;
+    const double beta = active[b] != 0.0 ? safe_ratio(rz_new[b], rz[b]) : 0.0;
+    const size_t o = (size_t)b * n;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        p[o + i] = fma(beta, p[o + i], z[o + i]);
+}
+void be_pcg_p(stream_t st, size_t n, int B, double* p, const double* z, const double* rz_new, const double* rz,
+              const double* active, const int* done) {
+    k_pcg_p<<<dim3(bvec_blocks(n, B), B), kThreads, 0, (cudaStream_t)st>>>(n, p, z, rz_new, rz, active, done);
+    PDEOP_COUNT(1);
+    PDEOP_LAUNCH_CHECK();
+}
+
+__global__ void k_pcg_scalars(int B, double* active, double* rz, double* rz_new, double* pAp, double* rr, double* bnorm,
+                              double rtol, FgmresState* s, int first) {
+    __shared__ int any_active;
+    __shared__ double worst;
+    if (threadIdx.x == 0) {
+        any_active = 0;
+        worst = 0.0;
+    }
+    __syncthreads();
+    if (!first && s->done) return;
+    double my_worst = 0.0;
+    int my_any = 0;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        if (first) {
+            bnorm[b] = sqrt(rr[b]);
+            active[b] = bnorm[b] > 0.0 ? 1.0 : 0.0;   // cg.py:69 cont_mask
+            rz[b] = 0.0;
+        } else {
+            const double rel = bnorm[b] > 0.0 ? sqrt(rr[b]) / bnorm[b] : 0.0;
+            if (!(rel > rtol)) active[b] = 0.0;       // cg.py:131-133 res_mask
+            my_worst = fmax(my_worst, rel);
+            rz[b] = rz_new[b];
+        }
+        rz_new[b] = 0.0;
+        pAp[b] = 0.0;
+        rr[b] = 0.0;
+        if (active[b] != 0.0) my_any = 1;
+    }
+    if (my_any) atomicOr(&any_active, 1);
+    // max over the block through shared memory (values are non-negative: integer compare of the bit pattern)
+    atomicMax(reinterpret_cast<unsigned long long*>(&worst), (unsigned long long)__double_as_longlong(my_worst));
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (first) {
+            s->iters = 0;
+            s->rnorm = 0.0;
+        } else {
+            s->iters += 1;
+            s->rnorm = worst;
+        }
+        s->done = any_active ? 0 : 1;
+    }
+}
+void be_pcg_scalars(stream_t st, int B, double* active, double* rz, double* rz_new, double* pAp, double* rr,
+                    double* bnorm, double rtol, FgmresState* state, int first) {
+    k_pcg_scalars<<<1, 256, 0, (cudaStream_t)st>>>(B, active, rz, rz_new, pAp, rr, bnorm, rtol, state, first);
+    PDEOP_COUNT(1);
+    PDEOP_LAUNCH_CHECK();
+}
+
+__global__ void __launch_bounds__(kThreads) k_poly_update(size_t n, double* __restrict__ x, double* __restrict__ d,
+                                                          const double* __restrict__ r, const double* __restrict__ dinv,
+                                                          double c1, double c2, const double* lam, int mode,
+                                                          const int* done) {
+    if (done && *done) return;
+    const int b = blockIdx.y;
+    double c2b = c2;
+    if (mode == 1) c2b = c2 / lam[b];
+    else if (mode == 2) c2b = fmin(c2, 1.8 / lam[b]);
+    const size_t o = (size_t)b * n;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double dn = fma(c1, d[o + i], c2b * dinv[o + i] * r[o + i]);
+        d[o + i] = dn;
+        x[o + i] += dn;
+    }
+}
+void be_copy(stream_t st, void* dst, const void* src, size_t bytes) {
+    if (bytes) note(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)st));
+}
+void be_poly_update(stream_t st, size_t n, int B, double* x, double* d, const double* r, const double* dinv, double c1,
+                    double c2, const double* lam, int mode, const int* done) {
+    k_poly_update<<<dim3(bvec_blocks(n, B), B), kThreads, 0, (cudaStream_t)st>>>(n, x, d, r, dinv, c1, c2, lam, mode, done);
+    PDEOP_COUNT(1);
+    PDEOP_LAUNCH_CHECK();
+}
+
+// out (coarse) += P^T in (fine): every fine point scatters to the <= 8 coarse corners its prolongation reads
+__global__ void __launch_bounds__(kThreads) k_restrict_t(LevelDev Lf, LevelDev Lc, int C, const double* __restrict__ in,
+                                                         double* out, const int* done) {
+    if (done && *done) return;
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= Lf.G) return;
+    restrict_t_elem(Lf, Lc, C, in + (size_t)blockIdx.y * C * Lf.G, out + (size_t)blockIdx.y * C * Lc.G, w);
+}
+void be_restrict_t(stream_t st, const LevelDev& Lf, const LevelDev& Lc, int B, int C, const double* in, double* out,
+                   const int* done) {
+    note(cudaMemsetAsync(out, 0, (size_t)B * C * Lc.G * sizeof(double), (cudaStream_t)st));
+    k_restrict_t<<<dim3(cdiv(Lf.G, kThreads), B), kThreads, 0, (cudaStream_t)st>>>(Lf, Lc, C, in, out, done);
+    PDEOP_COUNT(1);
+    PDEOP_LAUNCH_CHECK();
+}
+
+__global__ void __launch_bounds__(kThreads) k_power_scale(size_t n, double* __restrict__ v, const double* __restrict__ Kv,
+                                                          const double* __restrict__ dinv, const double* nrm2, double* lam,
+                                                          int phase) {
+    const int b = blockIdx.y;
+    const size_t o = (size_t)b * n;
+    if (phase == 0) {   // v <- dinv .* Kv
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+            v[o + i] = dinv[o + i] * Kv[o + i];
+        return;
+    }
+    const double nn = sqrt(nrm2[b]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) lam[b] = nn;
+    const double inv = nn > 0.0 ? 1.0 / nn : 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        v[o + i] *= inv;
+}
+void be_power_step(stream_t st, size_t n, int B, double* v, const double* Kv, const double* dinv, double* lam,
+                   double* tmpB) {
+    cudaStream_t s = (cudaStream_t)st;
+    const dim3 grid(bvec_blocks(n, B), B);
+    k_power_scale<<<grid, kThreads, 0, s>>>(n, v, Kv, dinv, nullptr, lam, 0);
+    note(cudaMemsetAsync(tmpB, 0, sizeof(double) * B, s));
+    k_bdot<<<grid, kThreads, 0, s>>>(n, v, v, tmpB, nullptr);
+    k_power_scale<<<grid, kThreads, 0, s>>>(n, v, nullptr, nullptr, tmpB, lam, 1);
+    PDEOP_COUNT(3);
+    PDEOP_LAUNCH_CHECK();
+}
+
 void be_state_reset(stream_t st, FgmresState* s) {
     note(cudaMemsetAsync(s, 0, sizeof(FgmresState), (cudaStream_t)st));
 }

@@ -653,6 +653,35 @@ PDEOP_HD void interp_elem(const LevelDev& Li, const LevelDev& Lo, int C, const d
     }
 }
 
+// Transpose of the linear prolongation coarse -> fine: fine point wf adds w * in[wf] to every coarse corner its
+// prolongated value reads with weight w (R = P^T; the converged-mode V-cycle needs it to stay symmetric).
+PDEOP_HD void restrict_t_elem(const LevelDev& Lf, const LevelDev& Lc, int C, const double* __restrict__ in,
+                              double* out, int wf) {
+    int i0, i1, i2;
+    unpack_coord(Lf.coord[wf], i0, i1, i2);
+    int l[3], h[3];
+    double w0[3], w1[3];
+    interp_axis(i0, Lc.N[0], Lf.N[0], l[0], h[0], w0[0], w1[0]);
+    interp_axis(i1, Lc.N[1], Lf.N[1], l[1], h[1], w0[1], w1[1]);
+    interp_axis(i2, Lc.N[2], Lf.N[2], l[2], h[2], w0[2], w1[2]);
+    for (int c0 = 0; c0 < 2; ++c0) {
+        const double a0 = c0 ? w1[0] : w0[0];
+        if (a0 == 0.0) continue;
+        for (int c1 = 0; c1 < 2; ++c1) {
+            const double a1 = c1 ? w1[1] : w0[1];
+            if (a1 == 0.0) continue;
+            for (int c2 = 0; c2 < 2; ++c2) {
+                const double a2 = c2 ? w1[2] : w0[2];
+                if (a2 == 0.0) continue;
+                const int pc = wave_pos(Lc, c0 ? h[0] : l[0], c1 ? h[1] : l[1], c2 ? h[2] : l[2]);
+                const double wt = a0 * a1 * a2;
+                for (int m = 0; m < C; ++m)
+                    PDEOP_ATOMIC_ADD(&out[(size_t)m * Lc.G + pc], wt * in[(size_t)m * Lf.G + wf]);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // layout conversion between the operator surface (B,G,M) natural order and wave/planar order
 // ------------------------------------------------------------------------------------------------

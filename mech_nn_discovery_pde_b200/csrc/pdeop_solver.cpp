@@ -284,6 +284,9 @@ struct Scratch {
     size_t gs_stash_stride;
     std::vector<double*> lx, lb, lr;
     size_t n0;
+    // converged mode: per-instance scalars (8 arrays of B) and lambda_max estimates (one array of B per level)
+    double* bscal;
+    double* lam;
 };
 
 static size_t state_doubles() { return kStateAreaDoubles; }
@@ -296,6 +299,7 @@ static size_t scratch_doubles(const pdeop_plan* pl, int restart) {
     for (int l = 1; l < pl->n_grid; ++l) tot += 3 * (size_t)pl->B * pl->lev[l].dev.M * pl->lev[l].dev.G;
     tot += 2 * (size_t)pl->B * pl->nc;
     tot += (size_t)pl->B * be_gs_stash_doubles(L0);
+    tot += (size_t)pl->B * (8 + pl->n_grid);
     return tot;
 }
 
@@ -328,6 +332,9 @@ static Scratch carve(const pdeop_plan* pl, void* scratch, int restart) {
     s.cwork = p; p += 2 * (size_t)pl->B * pl->nc;
     s.gs_stash = p;
     s.gs_stash_stride = be_gs_stash_doubles(L0);
+    p += (size_t)pl->B * s.gs_stash_stride;
+    s.bscal = p; p += (size_t)pl->B * 8;
+    s.lam = p;
     return s;
 }
 
@@ -528,6 +535,140 @@ static void fgmres(pdeop_plan* pl, const pdeop_solver_cfg* cfg, void* persist, S
     }
 }
 
+// =================================================================================================
+// Converged mode: PCG with per-instance masks (solver/cg.py:51-147) preconditioned by a
+// symmetric V-cycle with a polynomial smoother (weighted Jacobi, solver/multigrid.py:407-416, or Chebyshev)
+// =================================================================================================
+static int check_pcg(const pdeop_pcg_cfg* c) {
+    if (!c) return fail("null cfg");
+    if (c->max_iter < 0 || c->sweeps < 1 || c->sweeps > 16 || c->power_iters < 1) return fail("bad PCG knob");
+    if (c->smoother != 0 && c->smoother != 1) return fail("smoother must be 0 (Jacobi) or 1 (Chebyshev)");
+    if (!(c->rtol >= 0.0) || !(c->jacobi_w > 0.0)) return fail("bad PCG tolerance / weight");
+    return 0;
+}
+
+
+// lam[l][b] ~ lambda_max(D^-1 K_l) by power iteration from a positive start vector (v = dinv .* dinv)
+static void estimate_lambda(pdeop_plan* pl, const pdeop_pcg_cfg* cfg, void* persist, Scratch& sc, stream_t st) {
+    const int B = pl->B;
+    for (int l = 0; l + 1 < pl->n_grid; ++l) {
+        const LevelDev& L = pl->lev[l].dev;
+        const size_t n = (size_t)L.M * L.G;
+        double* v = l == 0 ? sc.V : sc.lx[l];
+        double* Kv = l == 0 ? sc.w : sc.lr[l];
+        be_zero(st, v, (size_t)B * n * sizeof(double));
+        be_zero(st, Kv, (size_t)B * n * sizeof(double));
+        be_poly_update(st, n, B, v, Kv, P_dinv(pl, persist, l), P_dinv(pl, persist, l), 0.0, 1.0, nullptr, 0, nullptr);
+        double* lam = sc.lam + (size_t)l * B;
+        for (int it = 0; it < cfg->power_iters; ++it) {
+            be_apply_k(st, L, B, P_T(pl, persist, l), P_coef(pl, persist, l), v, nullptr, Kv, 0, nullptr);
+            be_power_step(st, n, B, v, Kv, P_dinv(pl, persist, l), lam, sc.bscal + 7 * (size_t)B);
+        }
+    }
+}
+
+// x <- x + p(D^-1 K)(b - K x): `sweeps` steps of the polynomial smoother on level l (r, d: temporaries).
+// Chebyshev over [1.1 lambda_max / 30, 1.1 lambda_max] (coefficients in units of lambda_max, the kernel divides by
+// the instance's estimate), or weighted Jacobi x += w D^-1 r with w = min(jacobi_w, 1.8 / lambda_max).
+static void smooth_poly(pdeop_plan* pl, const pdeop_pcg_cfg* cfg, void* persist, Scratch& sc, int l, const double* b,
+                        double* x, double* r, double* d, bool x_is_zero, stream_t st) {
+    const int B = pl->B;
+    const LevelDev& L = pl->lev[l].dev;
+    const size_t n = (size_t)L.M * L.G;
+    const int* done = &sc.state->done;
+    const double* lam = sc.lam + (size_t)l * B;
+    const double* dinv = P_dinv(pl, persist, l);
+    const double lmax = 1.1, lmin = 1.1 / (cfg->cheb_ratio > 1.0 ? cfg->cheb_ratio : 30.0);
+    const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+    double rho_prev = 1.0 / sigma;
+    ProfScope ps(pl->prof, l == 0 ? PC_GS_FINE : PC_GS_COARSE, st);
+    for (int k = 0; k < cfg->sweeps; ++k) {
+        const double* res = r;
+        if (k == 0 && x_is_zero) res = b;   // r = b - K 0
+        else be_apply_k(st, L, B, P_T(pl, persist, l), P_coef(pl, persist, l), x, b, r, 1, done);
+        if (cfg->smoother == 0) {
+            if (k == 0) be_zero(st, d, (size_t)B * n * sizeof(double));
+            be_poly_update(st, n, B, x, d, res, dinv, 0.0, cfg->jacobi_w, lam, 2, done);
+        } else if (k == 0) {
+            be_zero(st, d, (size_t)B * n * sizeof(double));
+            be_poly_update(st, n, B, x, d, res, dinv, 0.0, 1.0 / theta, lam, 1, done);
+        } else {
+            const double rho = 1.0 / (2.0 * sigma - rho_prev);
+            be_poly_update(st, n, B, x, d, res, dinv, rho * rho_prev, 2.0 * rho / delta, lam, 1, done);
+            rho_prev = rho;
+        }
+    }
+}
+
+// z = M^-1 b: symmetric V-cycle from a zero guess (pre- and post-smoother are the same polynomial, R = P^T)
+static void vcycle_sym(pdeop_plan* pl, const pdeop_pcg_cfg* cfg, void* persist, Scratch& sc, int l, const double* b,
+                       double* x, double* r, double* d, stream_t st) {
+    const int B = pl->B;
+    const LevelDev& L = pl->lev[l].dev;
+    const size_t n = (size_t)L.M * L.G;
+    const int* done = &sc.state->done;
+    be_zero(st, x, (size_t)B * n * sizeof(double));
+    smooth_poly(pl, cfg, persist, sc, l, b, x, r, d, true, st);
+    {
+        ProfScope ps(pl->prof, l == 0 ? PC_APPLY_FINE : PC_APPLY_COARSE, st);
+        be_apply_k(st, L, B, P_T(pl, persist, l), P_coef(pl, persist, l), x, b, r, 1, done);
+    }
+    const LevelDev& Lc = pl->lev[l + 1].dev;
+    {
+        ProfScope ps(pl->prof, PC_TRANSFER, st);
+        be_restrict_t(st, L, Lc, B, L.M, r, sc.lb[l + 1], done);
+    }
+    if (l + 1 == pl->n_grid - 1) {
+        ProfScope ps(pl->prof, PC_COARSE_SOLVE, st);
+        be_chol_solve(st, Lc, B, P_Kd(pl, persist, sc), P_Linv(pl, persist), sc.lb[l + 1], sc.lx[l + 1], sc.cwork, done,
+                      pl->use_chain);
+    } else {
+        // level l+1 temporaries: r = lr[l+1], d = slice l+1 of Z (the reference mode's Krylov basis, idle here)
+        vcycle_sym(pl, cfg, persist, sc, l + 1, sc.lb[l + 1], sc.lx[l + 1], sc.lr[l + 1],
+                   sc.Z + (size_t)(l + 1) * sc.n0, st);
+    }
+    {
+        ProfScope ps(pl->prof, PC_TRANSFER, st);
+        be_interp(st, Lc, L, B, L.M, sc.lx[l + 1], x, 1, done);
+    }
+    smooth_poly(pl, cfg, persist, sc, l, b, x, r, d, false, st);
+}
+
+// x = K^-1 b per instance to ||r_b|| <= rtol ||b_b||.  Vectors: b = sc.atb, x = sc.x, Ap = sc.w, r/z/p = V[0..2],
+// level-0 smoother temporaries V[3] (r) and Z[0] (d).
+static void pcg(pdeop_plan* pl, const pdeop_pcg_cfg* cfg, void* persist, Scratch& sc, const double* b, double* x,
+                stream_t st) {
+    const int B = pl->B;
+    const LevelDev& L0 = pl->lev[0].dev;
+    const size_t n = (size_t)L0.M * L0.G;
+    const int* done = &sc.state->done;
+    double *r = sc.V, *z = sc.V + sc.n0, *p = sc.V + 2 * sc.n0, *sr = sc.V + 3 * sc.n0, *sd = sc.Z;
+    double *active = sc.bscal, *rz = active + B, *rz_new = rz + B, *pAp = rz_new + B, *rr = pAp + B, *bnorm = rr + B;
+    estimate_lambda(pl, cfg, persist, sc, st);
+    be_zero(st, x, sc.n0 * sizeof(double));
+    be_zero(st, sc.bscal, sizeof(double) * 8 * B);
+    be_bdot(st, n, B, b, b, rr, nullptr);
+    be_pcg_scalars(st, B, active, rz, rz_new, pAp, rr, bnorm, cfg->rtol, sc.state, 1);
+    be_copy(st, r, b, sc.n0 * sizeof(double));
+    be_zero(st, p, sc.n0 * sizeof(double));
+    for (int it = 0; it < cfg->max_iter; ++it) {
+        vcycle_sym(pl, cfg, persist, sc, 0, r, z, sr, sd, st);
+        {
+            ProfScope pk(pl->prof, PC_KRYLOV, st);
+            be_bdot(st, n, B, r, z, rz_new, done);
+            be_pcg_p(st, n, B, p, z, rz_new, rz, active, done);   // first iteration: rz = 0 => beta = 0, p = z
+        }
+        {
+            ProfScope pa(pl->prof, PC_APPLY_FINE, st);
+            be_apply_k(st, L0, B, P_T(pl, persist, 0), P_coef(pl, persist, 0), p, nullptr, sc.w, 0, done);
+        }
+        ProfScope pk(pl->prof, PC_KRYLOV, st);
+        be_bdot(st, n, B, p, sc.w, pAp, done);
+        be_pcg_xr(st, n, B, x, r, p, sc.w, rz_new, pAp, active, rr, done);   // alpha = (r.z) / (p.Kp)
+        be_pcg_scalars(st, B, active, rz, rz_new, pAp, rr, bnorm, cfg->rtol, sc.state, 0);
+    }
+}
+
 static int check_cfg(const pdeop_solver_cfg* cfg) {
     if (!cfg) return fail("null cfg");
     if (cfg->restart < 1 || cfg->restart > kMaxRestart) return fail("restart must be in [1,32]");
@@ -587,6 +728,39 @@ extern "C" int pdeop_mg_backward(pdeop_plan* pl, const pdeop_solver_cfg* cfg, co
     be_state_reset(stream, sc.state);
     be_pack(stream, pl->lev[0].dev, pl->B, grad_x, sc.atb);
     fgmres(pl, cfg, persist, sc, sc.atb, sc.x, stream);   // dz, same operator and preconditioner (:95)
+    if (info_out) be_fg_info(stream, sc.state, info_out);
+    run_grads(pl, persist, sc, rhs, cv0, fv0, bv0, x, sc.x, d_coeffs, d_rhs, d_iv_rhs, d_cv, d_fv, d_bv, stream);
+    return check_backend();
+}
+
+extern "C" int pdeop_mg_forward_converged(pdeop_plan* pl, const pdeop_pcg_cfg* cfg, const double* coeffs,
+                                          const double* rhs, const double* iv_rhs, const double* const* cv,
+                                          const double* const* fv, const double* const* bv, void* persist,
+                                          void* scratch, double* x_out, double* info_out, void* stream) {
+    if (check_plan(pl)) return 1;
+    if (pl->n_grid < 2) return fail("multigrid path needs n_grid >= 2");
+    if (check_pcg(cfg)) return 1;
+    Scratch sc = carve(pl, scratch, std::max(5, pl->n_grid + 1));
+    setup_operator(pl, coeffs, cv, fv, bv, persist, sc, stream);
+    be_atb(stream, pl->lev[0].dev, pl->B, P_coef(pl, persist, 0), rhs, iv_rhs, sc.atb);
+    pcg(pl, cfg, persist, sc, sc.atb, sc.x, stream);
+    be_unpack(stream, pl->lev[0].dev, pl->B, sc.x, x_out);
+    if (info_out) be_fg_info(stream, sc.state, info_out);
+    return check_backend();
+}
+
+extern "C" int pdeop_mg_backward_converged(pdeop_plan* pl, const pdeop_pcg_cfg* cfg, const double* rhs, const double* cv0,
+                                           const double* fv0, const double* bv0, void* persist, void* scratch,
+                                           const double* x, const double* grad_x, double* d_coeffs, double* d_rhs,
+                                           double* d_iv_rhs, double* d_cv, double* d_fv, double* d_bv, double* info_out,
+                                           void* stream) {
+    if (check_plan(pl)) return 1;
+    if (pl->n_grid < 2) return fail("multigrid path needs n_grid >= 2");
+    if (check_pcg(cfg)) return 1;
+    Scratch sc = carve(pl, scratch, std::max(5, pl->n_grid + 1));
+    be_state_reset(stream, sc.state);
+    be_pack(stream, pl->lev[0].dev, pl->B, grad_x, sc.atb);
+    pcg(pl, cfg, persist, sc, sc.atb, sc.x, stream);
     if (info_out) be_fg_info(stream, sc.state, info_out);
     run_grads(pl, persist, sc, rhs, cv0, fv0, bv0, x, sc.x, d_coeffs, d_rhs, d_iv_rhs, d_cv, d_fv, d_bv, stream);
     return check_backend();

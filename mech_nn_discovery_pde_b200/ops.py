@@ -144,17 +144,35 @@ class PdePlan:
 
 
 def knobs_of(config, back):
-    """[gs_pre, gs_post, mg_steps, max_iter, restart, gs_variant] from a PDEConfig-like object (config.py:13-29)."""
+    """[gs_pre, gs_post, mg_steps, max_iter, restart, gs_variant | mode, pcg_max_iter, smoother, sweeps, power_iters]
+    from a PDEConfig-like object (config.py:13-29); mode 1 = converged (per-instance PCG)."""
+    mode = {"reference": 0, "converged": 1}[getattr(config, "solver_mode", "reference")]
+    smoother = {"jacobi": 0, "chebyshev": 1}[getattr(config, "mg_smoother", "chebyshev")]
     return [int(config.mg_gauss_seidel_steps_pre), int(config.mg_gauss_seidel_steps_post),
             int(config.mg_steps_backward if back else config.mg_steps_forward),
             int(config.mg_fgmres_max_iter_backward if back else config.mg_fgmres_max_iter_forward),
             int(config.mg_fgmres_restarts_backward if back else config.mg_fgmres_restarts_forward),
-            int(getattr(config, "gs_variant", 0))]
+            int(getattr(config, "gs_variant", 0)),
+            mode, int(getattr(config, "mg_pcg_max_iter", 1000)), smoother, int(getattr(config, "mg_smoother_sweeps", 8)),
+            int(getattr(config, "mg_power_iters", 12))]
+
+
+def fparams_of(config):
+    """[atol (reference mode, fgmres.py:22), rtol (converged mode), jacobi_w (config.py:29), Chebyshev interval ratio]"""
+    return [float(getattr(config, "mg_fgmres_atol", 1e-5)), float(getattr(config, "mg_pcg_rtol", 1e-8)),
+            float(getattr(config, "jacobi_w", 0.4)), float(getattr(config, "mg_cheb_ratio", 30.0))]
+
+
+def _pcg_struct(knobs, fparams):
+    c = _lib.PcgCfg()
+    c.max_iter, c.smoother, c.sweeps, c.power_iters = int(knobs[7]), int(knobs[8]), int(knobs[9]), int(knobs[10])
+    c.rtol, c.jacobi_w, c.cheb_ratio = float(fparams[1]), float(fparams[2]), float(fparams[3])
+    return c
 
 
 def _cfg_struct(knobs, atol):
     c = _lib.SolverCfg()
-    c.gs_pre, c.gs_post, c.mg_steps, c.max_iter, c.restart, c.gs_variant = [int(v) for v in knobs]
+    c.gs_pre, c.gs_post, c.mg_steps, c.max_iter, c.restart, c.gs_variant = [int(v) for v in knobs[:6]]
     c.atol = float(atol)
     return c
 
@@ -188,7 +206,7 @@ def _raise_if_not_spd(info):
 # ---------------------------------------------------------------------------------------------------------------
 @torch.library.custom_op("pdeop::mg_solve", mutates_args=())
 def mg_solve(coeffs: Tensor, rhs: Tensor, iv_rhs: Tensor, cv: List[Tensor], fv: List[Tensor], bv: List[Tensor],
-             plan: int, knobs: List[int], knobs_bwd: List[int], atol: float,
+             plan: int, knobs: List[int], knobs_bwd: List[int], fparams: List[float],
              flags: int) -> Tuple[Tensor, Tensor, Tensor]:
     """x (B,n), persist, info[4] = FGMRES(A^T A, A^T b) with a V-cycle preconditioner
     (qp_dual_sparse_multigrid_normal_kkt.py:25-79).  cv/fv/bv: line values of every level."""
@@ -202,28 +220,31 @@ def mg_solve(coeffs: Tensor, rhs: Tensor, iv_rhs: Tensor, cv: List[Tensor], fv: 
     if not (len(cv) == len(fv) == len(bv) == pl.n_grid):
         raise ValueError("pdeop: one set of line values per multigrid level is required")
     dev = coeffs.device
-    cfg = _cfg_struct(knobs, atol)
-    scratch = pl.scratch(dev, max(int(knobs[4]), int(knobs_bwd[4])))
+    scratch = pl.scratch(dev, max(int(knobs[4]), int(knobs_bwd[4]), pl.n_grid + 1, 5))
     persist = pl.new_persist(dev)
     x = torch.empty(pl.batch, pl.n, dtype=torch.float64, device=dev)
     info = torch.zeros(4, dtype=torch.float64, device=dev)
+    args = (_lib._ptr(coeffs), _lib._ptr(rhs), _lib._ptr(iv_rhs), _ptr_array(cv), _ptr_array(fv), _ptr_array(bv),
+            _lib._ptr(persist), _lib._ptr(scratch), _lib._ptr(x), _lib._ptr(info), _lib.current_stream_ptr(dev))
     with pl.device_guard():
-        lib.check(lib.dll.pdeop_mg_forward(pl.handle, ctypes.byref(cfg), _lib._ptr(coeffs), _lib._ptr(rhs),
-                                           _lib._ptr(iv_rhs), _ptr_array(cv), _ptr_array(fv), _ptr_array(bv),
-                                           _lib._ptr(persist), _lib._ptr(scratch), _lib._ptr(x), _lib._ptr(info),
-                                           _lib.current_stream_ptr(dev)))
+        if knobs[6] == 1:     # converged mode: per-instance PCG
+            cfg = _pcg_struct(knobs, fparams)
+            lib.check(lib.dll.pdeop_mg_forward_converged(pl.handle, ctypes.byref(cfg), *args))
+        else:
+            cfg = _cfg_struct(knobs, fparams[0])
+            lib.check(lib.dll.pdeop_mg_forward(pl.handle, ctypes.byref(cfg), *args))
     return x, persist, info
 
 
 @mg_solve.register_fake
-def _(coeffs, rhs, iv_rhs, cv, fv, bv, plan, knobs, knobs_bwd, atol, flags):
+def _(coeffs, rhs, iv_rhs, cv, fv, bv, plan, knobs, knobs_bwd, fparams, flags):
     pl = plan_from_id(plan)
     return (coeffs.new_empty(pl.batch, pl.n), coeffs.new_empty(pl.persist_bytes // 8), coeffs.new_empty(4))
 
 
 @torch.library.custom_op("pdeop::mg_solve_backward", mutates_args=())
 def mg_solve_backward(grad_x: Tensor, x: Tensor, rhs: Tensor, cv0: Tensor, fv0: Tensor, bv0: Tensor, persist: Tensor,
-                      plan: int, knobs: List[int], atol: float
+                      plan: int, knobs: List[int], fparams: List[float]
                       ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     """(d_coeffs, d_rhs, d_iv_rhs, d_cv, d_fv, d_bv, info) by implicit differentiation: dz = (A^T A)^-1 g with the
     same operator and preconditioner left in `persist` (qp_dual_sparse_multigrid_normal_kkt.py:81-162)."""
@@ -231,25 +252,28 @@ def mg_solve_backward(grad_x: Tensor, x: Tensor, rhs: Tensor, cv0: Tensor, fv0: 
     lib = pl.lib
     dev = x.device
     grad_x = grad_x.to(torch.float64).contiguous()
-    cfg = _cfg_struct(knobs, atol)
-    scratch = pl.scratch(dev, int(knobs[4]))
+    scratch = pl.scratch(dev, max(int(knobs[4]), pl.n_grid + 1, 5))
     B = pl.batch
     d_coeffs = torch.empty(B, pl.G, pl.M, dtype=torch.float64, device=dev)
     d_rhs = torch.empty(B, pl.G, dtype=torch.float64, device=dev)
     d_iv = torch.empty(B, pl.n_init, dtype=torch.float64, device=dev)
     d_cv, d_fv, d_bv = torch.empty_like(cv0), torch.empty_like(fv0), torch.empty_like(bv0)
     info = torch.zeros(4, dtype=torch.float64, device=dev)
+    args = (_lib._ptr(rhs), _lib._ptr(cv0), _lib._ptr(fv0), _lib._ptr(bv0), _lib._ptr(persist), _lib._ptr(scratch),
+            _lib._ptr(x), _lib._ptr(grad_x), _lib._ptr(d_coeffs), _lib._ptr(d_rhs), _lib._ptr(d_iv), _lib._ptr(d_cv),
+            _lib._ptr(d_fv), _lib._ptr(d_bv), _lib._ptr(info), _lib.current_stream_ptr(dev))
     with pl.device_guard():
-        lib.check(lib.dll.pdeop_mg_backward(pl.handle, ctypes.byref(cfg), _lib._ptr(rhs), _lib._ptr(cv0),
-                                            _lib._ptr(fv0), _lib._ptr(bv0), _lib._ptr(persist), _lib._ptr(scratch),
-                                            _lib._ptr(x), _lib._ptr(grad_x), _lib._ptr(d_coeffs), _lib._ptr(d_rhs),
-                                            _lib._ptr(d_iv), _lib._ptr(d_cv), _lib._ptr(d_fv), _lib._ptr(d_bv),
-                                            _lib._ptr(info), _lib.current_stream_ptr(dev)))
+        if knobs[6] == 1:
+            cfg = _pcg_struct(knobs, fparams)
+            lib.check(lib.dll.pdeop_mg_backward_converged(pl.handle, ctypes.byref(cfg), *args))
+        else:
+            cfg = _cfg_struct(knobs, fparams[0])
+            lib.check(lib.dll.pdeop_mg_backward(pl.handle, ctypes.byref(cfg), *args))
     return d_coeffs, d_rhs, d_iv, d_cv, d_fv, d_bv, info
 
 
 @mg_solve_backward.register_fake
-def _(grad_x, x, rhs, cv0, fv0, bv0, persist, plan, knobs, atol):
+def _(grad_x, x, rhs, cv0, fv0, bv0, persist, plan, knobs, fparams):
     pl = plan_from_id(plan)
     B = pl.batch
     return (x.new_empty(B, pl.G, pl.M), x.new_empty(B, pl.G), x.new_empty(B, pl.n_init), torch.empty_like(cv0),
@@ -323,9 +347,9 @@ _LAST_BWD_INFO = {}
 
 
 def _mg_setup_context(ctx, inputs, output):
-    coeffs, rhs, iv_rhs, cv, fv, bv, plan, knobs, knobs_bwd, atol, flags = inputs
+    coeffs, rhs, iv_rhs, cv, fv, bv, plan, knobs, knobs_bwd, fparams, flags = inputs
     x, persist, info = output
-    ctx.plan, ctx.knobs_bwd, ctx.atol, ctx.flags, ctx.n_levels = plan, list(knobs_bwd), atol, flags, len(cv)
+    ctx.plan, ctx.knobs_bwd, ctx.fparams, ctx.flags, ctx.n_levels = plan, list(knobs_bwd), list(fparams), flags, len(cv)
     ctx.save_for_backward(rhs, cv[0], fv[0], bv[0], x, persist, info)
 
 
@@ -334,7 +358,7 @@ def _mg_backward(ctx, grad_x, grad_persist, grad_info):
     if ctx.flags & FLAG_CHECK_SPD:
         _raise_if_not_spd(info)   # lazily: the forward never synchronises the host (cholesky_ex check, multigrid.py:439)
     d_coeffs, d_rhs, d_iv, d_cv, d_fv, d_bv, info_b = torch.ops.pdeop.mg_solve_backward(
-        grad_x, x, rhs, cv0, fv0, bv0, persist, ctx.plan, ctx.knobs_bwd, ctx.atol)
+        grad_x, x, rhs, cv0, fv0, bv0, persist, ctx.plan, ctx.knobs_bwd, ctx.fparams)
     _LAST_BWD_INFO[ctx.plan] = info_b
     if ctx.flags & FLAG_RHS_FP32:
         d_rhs = d_rhs.float().double()
@@ -405,8 +429,7 @@ def mg_solve_call(coeffs, rhs, iv_rhs, cv, fv, bv, holder):
     fvs = [fv] + [t[1] for t in holder.coarse]
     bvs = [bv] + [t[2] for t in holder.coarse]
     x, _persist, info = torch.ops.pdeop.mg_solve(coeffs, rhs, iv_rhs, cvs, fvs, bvs, plan.id, knobs_of(config, False),
-                                                 knobs_of(config, True),
-                                                 float(getattr(config, "mg_fgmres_atol", 1e-5)), config_flags(config))
+                                                 knobs_of(config, True), fparams_of(config), config_flags(config))
     holder.info_fwd = info.detach()
     return x
 

@@ -63,6 +63,10 @@ class PDEDenseLayer(nn.Module):
             iv_rhs = rhs.new_zeros(B, 0)
         for i in range(self.n_coord):   # pde_layer_dense.py:95-97
             steps_list[i] = steps_list[i].reshape(B, self.coord_dims[i] - 1)
+        # solver_dbl=False (pde_layer_dense.py:64-69,101-105: the reference then factors A^T A in the inputs' precision):
+        # here fp32 is a STORAGE format only -- operands are widened, the normal equations (cond ~1e10)
+        # are formed, factored and solved in fp64, and the results are rounded back to the inputs' dtype
+        out_dtype = torch.float64 if self.solver_dbl else coeffs.dtype
         coeffs = coeffs.double()
         rhs = rhs.double()
         iv_rhs = iv_rhs.double()
@@ -76,6 +80,8 @@ class PDEDenseLayer(nn.Module):
         eps = None
         u = self.pde.get_solution_reshaped(x)
         u = u.reshape(self.bs, self.n_ind_dim, *u.shape[1:])
+        if u.dtype != out_dtype:
+            u = u.to(out_dtype)
         u0 = u[:, :, :, 0]
         return u0, u, eps
 

@@ -10,6 +10,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <cmath>
 #include <vector>
 
 #include "../../mech_nn_discovery_pde_b200/csrc/pdeop_backend.h"
@@ -34,6 +36,101 @@ long long be_launch_count() { return 0; }
 int be_current_device() { return -1; }
 int be_default_gs_pipe() { return 2; }
 bool be_default_chain() { return false; }
+
+
+// ---- converged mode (plain loops; same semantics as the CUDA kernels) ----
+void be_copy(stream_t, void* dst, const void* src, size_t bytes) { if (bytes) memcpy(dst, src, bytes); }
+void be_bdot(stream_t, size_t n, int B, const double* a, const double* c, double* out, const int* done) {
+    if (done && *done) return;
+    for (int b = 0; b < B; ++b) {
+        double acc = 0.0;
+        for (size_t i = 0; i < n; ++i) acc += a[b * n + i] * c[b * n + i];
+        out[b] += acc;
+    }
+}
+static double safe_ratio(double a, double b) {
+    const double q = a / b;
+    return std::isfinite(q) ? q : 0.0;
+}
+void be_pcg_xr(stream_t, size_t n, int B, double* x, double* r, const double* p, const double* Ap, const double* rz,
+               const double* pAp, const double* active, double* rr, const int* done) {
+    if (done && *done) return;
+    for (int b = 0; b < B; ++b) {
+        const double alpha = active[b] != 0.0 ? safe_ratio(rz[b], pAp[b]) : 0.0;
+        double acc = 0.0;
+        for (size_t i = 0; i < n; ++i) {
+            x[b * n + i] += alpha * p[b * n + i];
+            r[b * n + i] -= alpha * Ap[b * n + i];
+            acc += r[b * n + i] * r[b * n + i];
+        }
+        rr[b] += acc;
+    }
+}
+void be_pcg_p(stream_t, size_t n, int B, double* p, const double* z, const double* rz_new, const double* rz,
+              const double* active, const int* done) {
+    if (done && *done) return;
+    for (int b = 0; b < B; ++b) {
+        const double beta = active[b] != 0.0 ? safe_ratio(rz_new[b], rz[b]) : 0.0;
+        for (size_t i = 0; i < n; ++i) p[b * n + i] = z[b * n + i] + beta * p[b * n + i];
+    }
+}
+void be_pcg_scalars(stream_t, int B, double* active, double* rz, double* rz_new, double* pAp, double* rr, double* bnorm,
+                    double rtol, FgmresState* s, int first) {
+    if (!first && s->done) return;
+    int any = 0;
+    double worst = 0.0;
+    for (int b = 0; b < B; ++b) {
+        if (first) {
+            bnorm[b] = sqrt(rr[b]);
+            active[b] = bnorm[b] > 0.0 ? 1.0 : 0.0;
+            rz[b] = 0.0;
+        } else {
+            const double rel = bnorm[b] > 0.0 ? sqrt(rr[b]) / bnorm[b] : 0.0;
+            if (!(rel > rtol)) active[b] = 0.0;
+            worst = std::max(worst, rel);
+            rz[b] = rz_new[b];
+        }
+        rz_new[b] = pAp[b] = rr[b] = 0.0;
+        if (active[b] != 0.0) any = 1;
+    }
+    if (first) { s->iters = 0; s->rnorm = 0.0; } else { s->iters += 1; s->rnorm = worst; }
+    s->done = any ? 0 : 1;
+}
+void be_poly_update(stream_t, size_t n, int B, double* x, double* d, const double* r, const double* dinv, double c1,
+                    double c2, const double* lam, int mode, const int* done) {
+    if (done && *done) return;
+    for (int b = 0; b < B; ++b) {
+        double c2b = c2;
+        if (mode == 1) c2b = c2 / lam[b];
+        else if (mode == 2) c2b = std::min(c2, 1.8 / lam[b]);
+        for (size_t i = 0; i < n; ++i) {
+            const double dn = c1 * d[b * n + i] + c2b * dinv[b * n + i] * r[b * n + i];
+            d[b * n + i] = dn;
+            x[b * n + i] += dn;
+        }
+    }
+}
+void be_restrict_t(stream_t, const LevelDev& Lf, const LevelDev& Lc, int B, int C, const double* in, double* out,
+                   const int* done) {
+    if (done && *done) return;
+    memset(out, 0, (size_t)B * C * Lc.G * sizeof(double));
+    for (int b = 0; b < B; ++b)
+        for (int w = 0; w < Lf.G; ++w)
+            restrict_t_elem(Lf, Lc, C, in + (size_t)b * C * Lf.G, out + (size_t)b * C * Lc.G, w);
+}
+void be_power_step(stream_t, size_t n, int B, double* v, const double* Kv, const double* dinv, double* lam, double*) {
+    for (int b = 0; b < B; ++b) {
+        double nn = 0.0;
+        for (size_t i = 0; i < n; ++i) {
+            v[b * n + i] = dinv[b * n + i] * Kv[b * n + i];
+            nn += v[b * n + i] * v[b * n + i];
+        }
+        nn = sqrt(nn);
+        lam[b] = nn;
+        const double inv = nn > 0.0 ? 1.0 / nn : 0.0;
+        for (size_t i = 0; i < n; ++i) v[b * n + i] *= inv;
+    }
+}
 
 static inline size_t vstride(const LevelDev& L) { return (size_t)L.M * L.G; }
 static inline size_t tstride(const LevelDev& L) { return (size_t)L.D * kTabEntries * kTabPitch; }

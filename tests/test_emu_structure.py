@@ -281,3 +281,53 @@ def run_surface_case(lib, device, name):
 @pytest.mark.parametrize("name", SURFACE_CASES)
 def test_surface_order1_and_n_ind_dim(name):
     run_surface_case(emu_library(), "cpu", name)
+
+
+def _converged_case(lib, device, dims, iv_name, B, n_grid, dsf, smoother, seed=123):
+    """Converged mode (per-instance PCG, symmetric V-cycle) against the EXACT least-squares solution: the dense
+    layer's Cholesky solve of the same system (semantics of solver/cg.py:51-147)."""
+    import torch
+    from oracle import pde_oracle as O
+    from oracle.cases import IV_LISTS, make_inputs
+    from mech_nn_discovery_pde_b200 import MultigridLayer, PDEConfig
+
+    class Cfg(PDEConfig):
+        solver_mode = "converged"
+        mg_pcg_rtol = 1e-8
+        mg_pcg_max_iter = 2500
+        mg_smoother = smoother
+        mg_smoother_sweeps = 8
+
+    iv = IV_LISTS[iv_name]
+    st = O.build_structure(dims, iv)
+    inp = make_inputs(dims, B, st.n_init, seed=seed)
+    inp["rhs"][1] *= 1e-3          # instances converge at different iterations: exercises the per-instance masks
+    dev = torch.device(device)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).to(dev)
+    layer = MultigridLayer(bs=B, coord_dims=dims, order=2, n_ind_dim=1, n_iv=1, n_grid=n_grid, downsample_first=dsf,
+                           init_index_mi_list=iv, n_iv_steps=1, _library=lib)
+    layer.config = Cfg
+    coeffs = t(inp["coeffs"]).requires_grad_(True)
+    rhs = t(inp["rhs"]).requires_grad_(True)
+    ivr = t(inp["iv_rhs"]).requires_grad_(True)
+    steps = [t(s).requires_grad_(True) for s in inp["steps"]]
+    u0, u, _ = layer(coeffs, rhs, ivr, list(steps))
+    (u * t(inp["loss_w"]).reshape(u.shape)).sum().backward()
+    f, b = layer.solver_info()
+    exact = O.dense_layer(dims, iv, inp["coeffs"], inp["rhs"], inp["iv_rhs"], inp["steps"],
+                          grad_out=inp["loss_w"].reshape(B, -1))
+    # every instance reached the relative tolerance before the cap, forward and backward
+    assert f[0] < Cfg.mg_pcg_max_iter and f[1] <= Cfg.mg_pcg_rtol, f
+    assert b[0] < Cfg.mg_pcg_max_iter and b[1] <= Cfg.mg_pcg_rtol, b
+    x = u.detach().cpu().numpy().reshape(B, -1)
+    for i in range(B):      # per instance: small instances are not hidden behind large ones
+        assert rel(x[i], exact.x[i]) < 1e-6
+    assert rel(coeffs.grad.cpu().numpy(), exact.d_coeffs) < 1e-5
+    assert rel(rhs.grad.cpu().numpy(), exact.d_rhs) < 1e-5
+    assert rel(ivr.grad.cpu().numpy(), exact.d_iv_rhs) < 1e-5
+    return f, b
+
+
+@pytest.mark.parametrize("smoother", ["chebyshev", "jacobi"])
+def test_converged_mode_vs_exact_solution(smoother):
+    _converged_case(emu_library(), "cpu", (16, 16), "burgers", 3, 2, True, smoother)

@@ -509,3 +509,39 @@ def test_wrong_device_is_an_error(lib):
         cfg = sr.plan.cfg(False)
         rc = lib.dll.pdeop_stage(sr.plan.handle, ctypes.byref(cfg), _lib.STAGE_APPLY_K, 0, 0, None, None, None, None, None, None)
         assert rc != 0 and b"device" in lib.dll.pdeop_last_error()
+
+
+def test_fp32_storage_mode(lib):
+    """solver_dbl=False with fp32 tensors (pde_layer_dense.py:64-69,101-105): fp32 in and out, fp64 inside.  The result
+    is the fp64 solve of the fp32-rounded inputs rounded to fp32 (1e-6), and within the north star's 1e-4 of the fp64
+    oracle on the unrounded inputs (Kamani-sized system)."""
+    from mech_nn_discovery_pde_b200 import PDEDenseLayer
+    dims, B = (24,), 64
+    iv = IV_LISTS["kamani"]
+    st = O.build_structure(dims, iv)
+    inp = make_inputs(dims, B, st.n_init, seed=91)
+    dev = torch.device("cuda:0")
+    f32 = lambda a: torch.as_tensor(a, dtype=torch.float32, device=dev)
+    layer = PDEDenseLayer(bs=B, coord_dims=dims, order=2, n_ind_dim=1, n_iv=1, init_index_mi_list=iv, n_iv_steps=1,
+                          solver_dbl=False)
+    coeffs = f32(inp["coeffs"]).requires_grad_(True)
+    u0, u, _ = layer(coeffs, f32(inp["rhs"]), f32(inp["iv_rhs"]), [f32(s) for s in inp["steps"]])
+    assert u.dtype == torch.float32 and u0.dtype == torch.float32
+    (u * f32(inp["loss_w"]).reshape(u.shape)).sum().backward()
+    assert coeffs.grad.dtype == torch.float32 and torch.isfinite(coeffs.grad).all()
+    layer64 = PDEDenseLayer(bs=B, coord_dims=dims, order=2, n_ind_dim=1, n_iv=1, init_index_mi_list=iv, n_iv_steps=1)
+    up = lambda a: f32(a).double()
+    _, u64, _ = layer64(up(inp["coeffs"]), up(inp["rhs"]), up(inp["iv_rhs"]), [up(s) for s in inp["steps"]])
+    assert rel(u.double().cpu().numpy(), u64.cpu().numpy()) < 1e-6
+    ref = O.dense_layer(dims, iv, inp["coeffs"], inp["rhs"], inp["iv_rhs"], inp["steps"])
+    assert rel(u.double().cpu().numpy().reshape(B, -1), ref.x) < 1e-4
+
+
+@pytest.mark.parametrize("case", [((16, 16), "burgers", 2, True, "chebyshev"), ((16, 16), "burgers", 2, True, "jacobi"),
+                                  ((8, 16, 16), "gl", 2, False, "chebyshev")])
+def test_converged_mode_vs_exact_solution(lib, case):
+    """Converged mode (per-instance PCG, symmetric V-cycle with Chebyshev / weighted-Jacobi smoother, R = P^T): every
+    instance reaches its relative tolerance, and solution and gradients equal the exact least-squares solution."""
+    from tests.test_emu_structure import _converged_case
+    dims, ivn, n_grid, dsf, smoother = case
+    _converged_case(lib, "cuda:0", dims, ivn, 3, n_grid, dsf, smoother)
