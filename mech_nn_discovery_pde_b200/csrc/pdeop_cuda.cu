@@ -613,8 +613,8 @@ static int num_sms() {
 struct GsEnv {
     int threads, smem, single, pipe;
     GsEnv() {
-        // 128 registers/thread; 256/384/1024-thread variants were measured and are not faster, and 768 threads
-        // (80 registers, 300 bytes of spills) take 4.2 instead of 2.9 ms per fine-level call
+        // 128 registers/thread; 256/384/1024-thread variants were measured and are not faster; 576 / 640 threads
+        // (96 registers, ~150 bytes of spills) take 2.93 / 3.07 instead of 2.31 ms per fine-level call, 768 threads 4.2 ms
         threads = 512;
         const char* m = getenv("PDEOP_GS_SMEM");
         smem = (m && atoi(m) == 0) ? 0 : 1;
