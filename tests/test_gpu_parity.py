@@ -532,9 +532,9 @@ def test_fp32_storage_mode(lib):
     layer64 = PDEDenseLayer(bs=B, coord_dims=dims, order=2, n_ind_dim=1, n_iv=1, init_index_mi_list=iv, n_iv_steps=1)
     up = lambda a: f32(a).double()
     _, u64, _ = layer64(up(inp["coeffs"]), up(inp["rhs"]), up(inp["iv_rhs"]), [up(s) for s in inp["steps"]])
-    assert rel(u.double().cpu().numpy(), u64.cpu().numpy()) < 1e-6
+    assert rel(u.detach().double().cpu().numpy(), u64.detach().cpu().numpy()) < 1e-6
     ref = O.dense_layer(dims, iv, inp["coeffs"], inp["rhs"], inp["iv_rhs"], inp["steps"])
-    assert rel(u.double().cpu().numpy().reshape(B, -1), ref.x) < 1e-4
+    assert rel(u.detach().double().cpu().numpy().reshape(B, -1), ref.x) < 1e-4
 
 
 @pytest.mark.parametrize("case", [((16, 16), "burgers", 2, True, "chebyshev"), ((16, 16), "burgers", 2, True, "jacobi"),
