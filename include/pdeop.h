@@ -180,7 +180,8 @@ long long pdeop_launch_count(void);
  *   key 0 "gs_pipe": 0 unsplit cluster Gauss-Seidel kernel on every level, 1 software-pipelined kernel on every
  *                    level, 2 (default) staged kernel (cp.async operand staging, all gathers of a point in flight) on
  *                    the latency-bound 3-D levels, 3 staged kernel wherever it fits, 4 software-pipelined kernel on
- *                    the latency-bound levels (round-1 default)
+ *                    the latency-bound levels (round-1 default), 5 line-marching kernel (a thread owns a grid line,
+ *                    neighbours from shared-memory rings filled by cp.async) wherever it fits, mode 2 elsewhere
  *   key 1 "chain"  : read-only (pdeop_plan_get_tuning); chosen at creation, see pdeop_plan_opts.chain
  * Returns 0, or nonzero with pdeop_last_error(). */
 int pdeop_plan_set_tuning(pdeop_plan* plan, int key, int value);

@@ -570,6 +570,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gs_pipe(LevelDev L, const double
 
 }  // namespace pdeop
 #include "pdeop_gs_fast.cuh"
+#include "pdeop_gs_line.cuh"
 namespace pdeop {
 
 // cross-check variant: one launch per step, no intra-kernel synchronisation
@@ -709,11 +710,69 @@ static bool launch_gs_fast(cudaLaunchConfig_t& cfg, const LevelDev& L, const dou
     return true;
 }
 
+// k_gs_line (pdeop_gs_line.cuh): returns false when the level does not fit it (1-D, rows longer than a CTA, lines
+// shorter than 16 points, more than 8 CTAs per instance, shared memory)
+template <int D, int PS>
+static bool launch_gs_line_ps(cudaStream_t s, const LevelDev& L, int B, const double* T, const double* coef,
+                              const double* dinv, const double* b, double* x, double* stash, int nsweeps,
+                              const int* done) {
+    LineGeom g;
+    if (!line_geom(L, nsweeps, PS, 8, (size_t)227 * 1024, kLineMaxThreads, g)) return false;
+    if (g.C != 1 && g.C != 2 && g.C != 4 && g.C != 8) return false;
+    if (g.C > 1 && !stash) return false;
+    auto kern = k_gs_line<D, PS>;
+    const size_t smem = (size_t)g.o_end * sizeof(double);
+    ensure_dyn_smem((const void*)kern, smem);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(B * g.C));
+    cfg.blockDim = dim3((unsigned)g.threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)g.C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g.C > 1 ? 1 : 0;
+    long long* flags = reinterpret_cast<long long*>(stash);
+    if (g.C > 1) note(cudaMemsetAsync(flags, 0, (size_t)B * kLineFlagWords * sizeof(long long), s));
+    LineStreams S;
+    line_streams(L, coef, dinv, b, x, S);
+    note(cudaLaunchKernelEx(&cfg, kern, L, g, T, S, x, flags, done));
+    return true;
+}
+
+template <int D>
+static bool launch_gs_line(cudaStream_t s, const LevelDev& L, int B, const double* T, const double* coef,
+                           const double* dinv, const double* b, double* x, double* stash, int nsweeps,
+                           const int* done) {
+    int maxn = L.N[0] > L.N[1] ? L.N[0] : L.N[1];
+    maxn = (maxn > L.N[2] ? maxn : L.N[2]) + 2 * kTabPad;
+    if (maxn <= 40) return launch_gs_line_ps<D, 40>(s, L, B, T, coef, dinv, b, x, stash, nsweeps, done);
+    if (maxn <= 72) return launch_gs_line_ps<D, 72>(s, L, B, T, coef, dinv, b, x, stash, nsweeps, done);
+    if (maxn <= 136) return launch_gs_line_ps<D, 136>(s, L, B, T, coef, dinv, b, x, stash, nsweeps, done);
+    if (maxn <= 264) return launch_gs_line_ps<D, 264>(s, L, B, T, coef, dinv, b, x, stash, nsweeps, done);
+    return false;
+}
+template <>
+bool launch_gs_line<1>(cudaStream_t, const LevelDev&, int, const double*, const double*, const double*, const double*,
+                       double*, double*, int, const int*) {
+    return false;
+}
+
 template <int D>
 static void launch_gs_cluster(cudaStream_t s, const LevelDev& L, int B, const double* T, const double* coef,
                               const double* dinv, const double* b, double* x, double* stash, size_t stash_stride,
                               int nsweeps, const int* done, int gs_pipe) {
     const GsEnv& env = gs_env();
+    // gs_pipe 5: the line-marching kernel wherever it fits, the mode-2 choice elsewhere (measured slower than the
+    // hyperplane kernels on every level, profiles/r2_gs_experiments.md: kept as a tested variant, not the default)
+    if (gs_pipe == 5) {
+        if (launch_gs_line<D>(s, L, B, T, coef, dinv, b, x, stash, nsweeps, done)) return;
+        gs_pipe = 2;
+    }
     const int threads = env.threads;
     const int per_sm = 1;   // CTAs per SM (register-limited: 128 regs/thread x 512 threads)
     int maxn = L.N[0] > L.N[1] ? L.N[0] : L.N[1];

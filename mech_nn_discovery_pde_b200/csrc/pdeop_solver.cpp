@@ -225,7 +225,7 @@ extern "C" int pdeop_plan_create_ex(int d, const int* dims, int order, int batch
     pdeop_plan* pl = new pdeop_plan();
     pl->device = be_current_device();
     pl->gs_pipe = (opts && opts->gs_pipe >= 0) ? opts->gs_pipe : be_default_gs_pipe();
-    if (pl->gs_pipe > 4) { delete pl; return fail("gs_pipe must be 0..4"); }
+    if (pl->gs_pipe > 5) { delete pl; return fail("gs_pipe must be 0..5"); }
     const bool want_chain = (opts && opts->chain >= 0) ? opts->chain != 0 : be_default_chain();
     pl->D = d;
     pl->M = 1 + 2 * d;
@@ -379,7 +379,7 @@ static int check_plan(const pdeop_plan* pl) {
 extern "C" int pdeop_plan_set_tuning(pdeop_plan* pl, int key, int value) {
     if (!pl) return fail("null plan");
     if (key == 0) {
-        if (value < 0 || value > 4) return fail("gs_pipe must be 0..4");
+        if (value < 0 || value > 5) return fail("gs_pipe must be 0..5");
         pl->gs_pipe = value;
         return 0;
     }

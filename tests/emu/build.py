@@ -10,7 +10,7 @@ OUT = os.path.join(HERE, "libpdeop_emu.so")
 
 def build(force=False):
     deps = SRC + [os.path.join(ROOT, "mech_nn_discovery_pde_b200", "csrc", f)
-                  for f in ("pdeop_elem.h", "pdeop_common.h", "pdeop_backend.h", "pdeop_lstsq.h")] + \
+                  for f in ("pdeop_elem.h", "pdeop_common.h", "pdeop_backend.h", "pdeop_lstsq.h", "pdeop_gs_line.h")] + \
         [os.path.join(ROOT, "include", "pdeop.h")]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
         return OUT

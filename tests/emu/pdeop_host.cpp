@@ -16,6 +16,9 @@
 
 #include "../../mech_nn_discovery_pde_b200/csrc/pdeop_backend.h"
 #include "../../mech_nn_discovery_pde_b200/csrc/pdeop_elem.h"
+#include "../../mech_nn_discovery_pde_b200/csrc/pdeop_gs_line.h"
+
+#include <random>
 
 namespace pdeop {
 
@@ -205,10 +208,143 @@ static void gs_t(const LevelDev& L, int B, const double* T, const double* coef, 
             }
 }
 
+// ---- line-marching Gauss-Seidel (csrc/pdeop_gs_line.h) under a discrete-event model of the CUDA kernel ----
+// Every thread of every CTA of an instance is a little state machine over the phases A(0) B(0) A(1) B(1) ...; the
+// scheduler runs one phase of a randomly chosen runnable thread at a time, under exactly the ordering the kernel's
+// synchronisation provides and nothing more:
+//   * split CTA barrier: A(n+1) of a thread may run once every thread of its CTA has finished A(n);
+//   * cp.async: a copy issued in B(n) lands at a random moment between its issue and the end of the issuing thread's
+//     A(n+1) (where the kernel waits for it);
+//   * progress counters: thread 0 of a CTA publishes n at the start of its B(n) and may only continue once the
+//     neighbouring CTAs have published what B(n+2) needs (same formulas as the kernel).
+// A protocol error shows up as a result that differs from the sequential sweep, or as a deadlock (returns nonzero).
+static unsigned g_line_seed = 12345;
+static int g_line_maxthreads = 0;
+extern "C" void pdeop_emu_set_line_seed(unsigned v) { g_line_seed = v; }
+// test hook: fewer threads per CTA than the kernel uses, so that small grids span several CTAs
+extern "C" void pdeop_emu_set_line_max_threads(int v) { g_line_maxthreads = v; }
+static int g_line_last = 0;      // 1: the last be_gs call ran the line kernel model, -1: it deadlocked
+extern "C" int pdeop_emu_line_last() { return g_line_last; }
+
+struct LineHostIO {
+    std::vector<std::pair<double*, const double*>> pending;
+    double ldcg(const double* p) { return *p; }
+    void prefetch(const void*) {}
+    double ldstream(const double* p) { return *p; }
+    double ldown(const double* p) { return *p; }
+    void cp8(double* dst, const double* src) { pending.emplace_back(dst, src); }
+    void land(size_t k) {
+        *pending[k].first = *pending[k].second;
+        pending[k] = pending.back();
+        pending.pop_back();
+    }
+    void land_all() {
+        for (auto& pr : pending) *pr.first = *pr.second;
+        pending.clear();
+    }
+};
+
+template <int D, int PS>
+static int gs_line_model(const LevelDev& L, const LineGeom& g, const double* Ti, const LineStreams& S, unsigned ioff,
+                         double* x, std::mt19937& rng) {
+    const int C = g.C, NT = g.threads;
+    struct Th {
+        LineCtx<D> c;
+        LineHostIO io;
+        int pc = 0;   // next phase: 2n = A(n), 2n+1 = B(n)
+    };
+    std::vector<std::vector<double>> smem(C, std::vector<double>(g.o_end, 0.0));
+    std::vector<std::vector<Th>> th(C, std::vector<Th>(NT));
+    std::vector<std::vector<int>> fin_count(C, std::vector<int>(g.NS + 1, 0));   // threads that finished A(n)
+    std::vector<long long> flag(C, 0);
+    for (int q = 0; q < C; ++q) {
+        line_smem_fill<D, PS>(L, g, Ti, q, smem[q].data(), 0, 1);
+        for (int t = 0; t < NT; ++t) line_init<D>(L, g, q, t, th[q][t].c);
+    }
+    long long remaining = (long long)C * NT * 2 * g.NS;
+    std::vector<int> order((size_t)C * NT);
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    // may thread (q, t) run its next phase now?  (thread 0's publish is part of reaching B(n))
+    auto runnable = [&](int q, int t) -> bool {
+        Th& me = th[q][t];
+        if (me.pc >= 2 * g.NS) return false;
+        const int n = me.pc >> 1;
+        if ((me.pc & 1) == 0) return n == 0 || fin_count[q][n - 1] == NT;
+        if (C > 1 && t == 0) {
+            flag[q] = n;
+            if (q > 0 && flag[q - 1] < (long long)n + 3 - kLineDelta) return false;
+            if (q + 1 < C && flag[q + 1] < (long long)n + 8 + kLineDelta - g.N2) return false;
+        }
+        return true;
+    };
+    while (remaining > 0) {
+        std::shuffle(order.begin(), order.end(), rng);
+        bool progressed = false;
+        for (int id : order) {
+            const int q = id / NT, t = id % NT;
+            Th& me = th[q][t];
+            if (me.pc >= 2 * g.NS) continue;
+            if (rng() % 4 == 0) continue;   // random stalls: threads drift apart as far as the barriers allow
+            if (!runnable(q, t)) continue;
+            const int n = me.pc >> 1;
+            double* sm = smem[q].data();
+            while (!me.io.pending.empty() && rng() % 3 == 0) me.io.land(rng() % me.io.pending.size());
+            if ((me.pc & 1) == 0) {   // A(n), after WAIT(n-1)
+                line_fin<D, PS>(L, g, sm, x, me.c);
+                me.io.land_all();     // cp.async.wait_group 0 before ARRIVE(n)
+                fin_count[q][n] += 1;
+            } else {                  // B(n)
+                line_pre<D, PS>(L, g, sm, S, ioff, me.c, me.io);
+                line_advance<D>(g, me.c);
+            }
+            me.pc += 1;
+            remaining -= 1;
+            progressed = true;
+            if (me.pc == 2 * g.NS && t == 0) flag[q] = g.NS;
+        }
+        if (!progressed) {   // everything runnable was stalled at random -- or nothing is runnable: a deadlock
+            bool any = false;
+            for (int id : order) any = any || runnable(id / NT, id % NT);
+            if (!any) return -1;
+        }
+    }
+    return 0;
+}
+
+template <int D>
+static int gs_line_t(const LevelDev& L, int B, const double* T, const double* coef, const double* dinv, const double* b,
+                     double* x, int nsweeps) {
+    int maxn = std::max(L.N[0], std::max(L.N[1], L.N[2])) + 2 * kTabPad;
+    const int ps = maxn <= 40 ? 40 : maxn <= 72 ? 72 : maxn <= 136 ? 136 : maxn <= 264 ? 264 : 0;
+    LineGeom g;
+    if (!line_geom(L, nsweeps, ps, 8, (size_t)227 * 1024, g_line_maxthreads > 0 ? g_line_maxthreads : kLineMaxThreads, g))
+        return 0;
+    std::mt19937 rng(g_line_seed);
+    LineStreams S;
+    line_streams(L, coef, dinv, b, x, S);
+    for (int ib = 0; ib < B; ++ib) {
+        const double* Ti = T + ib * tstride(L);
+        const size_t o = ib * vstride(L);
+        int rc;
+        if (ps == 40) rc = gs_line_model<D, 40>(L, g, Ti, S, (unsigned)o, x + o, rng);
+        else if (ps == 72) rc = gs_line_model<D, 72>(L, g, Ti, S, (unsigned)o, x + o, rng);
+        else if (ps == 136) rc = gs_line_model<D, 136>(L, g, Ti, S, (unsigned)o, x + o, rng);
+        else rc = gs_line_model<D, 264>(L, g, Ti, S, (unsigned)o, x + o, rng);
+        if (rc) return -1;
+    }
+    return 1;
+}
+
 void be_gs(stream_t, const LevelDev& L, int B, const double* T, const double* coef, const double* dinv,
-           const double* b, double* x, double*, size_t, int nsweeps, const int* done, int, int) {
+           const double* b, double* x, double*, size_t, int nsweeps, const int* done, int variant, int gs_pipe) {
     if (done && *done) return;
     if (nsweeps <= 0) return;
+    g_line_last = 0;
+    if (variant == 0 && gs_pipe == 5 && L.D >= 2) {
+        g_line_last = L.D == 2 ? gs_line_t<2>(L, B, T, coef, dinv, b, x, nsweeps)
+                               : gs_line_t<3>(L, B, T, coef, dinv, b, x, nsweeps);
+        if (g_line_last != 0) return;
+    }
     if (L.D == 1) gs_t<1>(L, B, T, coef, dinv, b, x, nsweeps);
     else if (L.D == 2) gs_t<2>(L, B, T, coef, dinv, b, x, nsweeps);
     else gs_t<3>(L, B, T, coef, dinv, b, x, nsweeps);

@@ -331,3 +331,48 @@ def _converged_case(lib, device, dims, iv_name, B, n_grid, dsf, smoother, seed=1
 @pytest.mark.parametrize("smoother", ["chebyshev", "jacobi"])
 def test_converged_mode_vs_exact_solution(smoother):
     _converged_case(emu_library(), "cpu", (16, 16), "burgers", 3, 2, True, smoother)
+
+
+# dims, iv list, batch, n_grid, downsample_first, sweeps, threads per CTA of the model (0: the kernel's 512)
+LINE_CASES = [
+    ((16, 16, 16), "gl", 2, 2, True, 5, 0),      # one CTA per instance
+    ((16, 16, 16), "gl", 1, 2, True, 3, 64),     # four CTAs of four rows: progress counters, parked row
+    ((12, 16, 16), "gl", 1, 2, False, 3, 96),    # two CTAs of six rows
+    ((12, 16, 20), "gl", 1, 2, False, 1, 256),   # lines longer than rows, a single sweep, a CTA that is not full
+    ((16, 20, 16), "gl", 1, 2, False, 2, 80),    # rows that are not a multiple of the warp size
+    ((16, 16), "burgers", 2, 2, True, 5, 0),     # 2-D: one row
+    ((32, 24), "burgers", 1, 2, True, 3, 0),
+]
+
+
+@pytest.mark.parametrize("case", LINE_CASES)
+def test_line_marching_gs_matches_sequential_sweeps(case):
+    """The line-marching Gauss-Seidel kernel bodies (csrc/pdeop_gs_line.h) under the emulator's discrete-event model of
+    the CUDA kernel -- random thread interleavings within what the split CTA barrier, the cp.async waits and the
+    inter-CTA progress counters allow -- reproduce the sequential lexicographic sweeps bit for bit, for several random
+    schedules (solver/multigrid.py:399-405)."""
+    import ctypes
+    from oracle import pde_oracle as O
+    from oracle.cases import make_inputs
+    dims, ivn, B, n_grid, dsf, sweeps, max_threads = case
+    lib = emu_library()
+    iv = IV_LISTS[ivn]
+    st = O.build_structure(dims, iv)
+    inp = make_inputs(dims, B, st.n_init, seed=7)
+    sr = StageRunner(lib, "cpu", dims, iv, B, n_grid, dsf, inp["coeffs"], inp["steps"])
+    n = sr.level_n(0)
+    rng = np.random.default_rng(1)
+    b, x0 = rng.standard_normal(B * n), rng.standard_normal(B * n)
+    sr.plan.set_tuning("gs_pipe", 0)
+    ref = sr.stage(_lib.STAGE_GS, 0, b, x0, count=sweeps)
+    assert lib.dll.pdeop_emu_line_last() == 0
+    sr.plan.set_tuning("gs_pipe", 5)
+    lib.dll.pdeop_emu_set_line_max_threads(ctypes.c_int(max_threads))
+    try:
+        for seed in (1, 2, 3):
+            lib.dll.pdeop_emu_set_line_seed(ctypes.c_uint(seed))
+            got = sr.stage(_lib.STAGE_GS, 0, b, x0, count=sweeps)
+            assert lib.dll.pdeop_emu_line_last() == 1, "line kernel model not used, or it deadlocked"
+            assert np.array_equal(got, ref)
+    finally:
+        lib.dll.pdeop_emu_set_line_max_threads(ctypes.c_int(0))

@@ -376,12 +376,13 @@ def test_fgmres_control_flow(lib):
 
 
 def test_gs_kernel_variants_bit_identical(lib):
-    """The four Gauss-Seidel kernels (unsplit cluster kernel, software-pipelined kernel with the split cluster
-    barrier, cp.async-staged kernel with shared-memory table records, one launch per hyperplane step) run the same
+    """The five Gauss-Seidel kernels (unsplit cluster kernel, software-pipelined kernel with the split cluster
+    barrier, cp.async-staged kernel with shared-memory table records, line-marching kernel with shared-memory rings and
+    inter-CTA progress counters, one launch per hyperplane step) run the same
     canonical arithmetic: identical bits, on a level with one point per thread and step and on one with several
     rounds (register + global stash paths of the pipelined kernel); non-uniform steps exercise every table entry."""
     iv = IV_LISTS["gl"]
-    for dims, B, n_grid in (((8, 16, 16), 3, 2), ((32, 32, 32), 2, 3)):
+    for dims, B, n_grid in (((8, 16, 16), 3, 2), ((32, 32, 32), 2, 3), ((16, 64, 32), 2, 3)):
         G, M = int(np.prod(dims)), 7
         rng = np.random.default_rng(17)
         coeffs = np.zeros((B, G, M))
@@ -394,13 +395,16 @@ def test_gs_kernel_variants_bit_identical(lib):
         n = B * G * M
         b, x0 = rng.standard_normal(n), rng.standard_normal(n)
         outs = {}
-        for mode in (0, 1, 3):   # unsplit cluster kernel, software-pipelined kernel, staged kernel (k_gs_fast)
+        # unsplit cluster kernel, software-pipelined kernel, staged kernel (k_gs_fast), line-marching kernel (k_gs_line:
+        # 32x32x32 runs as 2 CTAs per instance, 16x64x32 as 2 CTAs of 8 rows; 8x16x16 does not fit it and falls back)
+        for mode in (0, 1, 3, 5):
             sr.plan.set_tuning("gs_pipe", mode)     # per-plan switch: nothing to restore for other plans
             outs[mode] = sr.stage(_lib.STAGE_GS, 0, b, x0, count=5)
         sr.plan.set_tuning("gs_pipe", 2)
         step_kernel = sr.stage(_lib.STAGE_GS, 0, b, x0, count=5, gs_variant=1)
         assert np.array_equal(outs[0], outs[1])
         assert np.array_equal(outs[0], outs[3])
+        assert np.array_equal(outs[0], outs[5])
         assert np.array_equal(outs[0], step_kernel)
 
 
