@@ -42,5 +42,7 @@ class PDEConfig:
     mg_pcg_max_iter = 1000
     mg_smoother = "chebyshev"      # or "jacobi" (weighted Jacobi with jacobi_w, solver/multigrid.py:407-416)
     mg_smoother_sweeps = 8
-    mg_power_iters = 12
+    # power iterations for lambda_max(D^-1 K): the estimate converges from below, and an under-estimate makes the
+    # Chebyshev smoother amplify the top of the spectrum (12 iterations: 3-D Ginzburg-Landau cases diverge; measured)
+    mg_power_iters = 60
     mg_cheb_ratio = 30.0           # Chebyshev smoothing interval [1.1 lambda_max / ratio, 1.1 lambda_max]

@@ -91,7 +91,14 @@ inline size_t be_chol_linv_doubles(int B, int n, int bw, bool use_chain) {
 // (bw = half-bandwidth of the matrix in the dense ordering; nothing outside the band is touched)
 // Linv: be_chol_linv_doubles(B, n, bw) doubles receiving the inverses of the diagonal blocks of L, their transposes
 // and, when the chain solver applies, the block-scaled band W = blockdiag(L_kk)^-1 L in two compact layouts
-void be_cholesky(stream_t st, int B, int n, int bw, double* Kd, double* Linv, FgmresState* state, bool use_chain);
+// aux: per-plan helper objects of the backend (be_aux_create), or nullptr: with them the panel factorisation of outer
+// panel k+1 runs on a second, higher-priority stream while the main stream applies panel k's trailing update to the
+// columns beyond panel k+1 (look-ahead); joined before the call returns control of the data to `st`
+void be_cholesky(stream_t st, int B, int n, int bw, double* Kd, double* Linv, FgmresState* state, bool use_chain,
+                 void* aux);
+// per-plan helper objects (CUDA build: one high-priority side stream and two events; emulator: nothing)
+void* be_aux_create();
+void be_aux_destroy(void* aux);
 // out = (L L^T)^-1 rhs for the dense system of level L (n = M*G); rhs/out in wave/planar layout, the
 // factor in band ordering; work: 2*B*n doubles
 void be_chol_solve(stream_t st, const LevelDev& L, int B, const double* Lf, const double* Linv, const double* rhs,

@@ -1874,7 +1874,58 @@ __global__ void __launch_bounds__(256) k_solve_small(int n, int B, const double*
         if (lane + 32 * r < n) out[(size_t)ib * n + lane + 32 * r] = y[r];
 }
 
-void be_cholesky(stream_t st, int B, int n, int bw, double* Kd, double* Linv, FgmresState* state, bool use_chain) {
+// Per-plan helper objects: a side stream (highest priority: its short, latency-bound panel kernels must win SM slots
+// against the main stream's deep updates) and two events.  PDEOP_FACTOR_LOOKAHEAD=0 disables the look-ahead (A/B).
+struct FactorAux {
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_cols = nullptr, ev_panel = nullptr;
+};
+void* be_aux_create() {
+    const char* e = getenv("PDEOP_FACTOR_LOOKAHEAD");
+    if (e && atoi(e) == 0) return nullptr;
+    FactorAux* a = new FactorAux();
+    int lo = 0, hi = 0;
+    note(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    note(cudaStreamCreateWithPriority(&a->side, cudaStreamNonBlocking, hi));
+    note(cudaEventCreateWithFlags(&a->ev_cols, cudaEventDisableTiming));
+    note(cudaEventCreateWithFlags(&a->ev_panel, cudaEventDisableTiming));
+    if (!a->side || !a->ev_cols || !a->ev_panel) {
+        be_aux_destroy(a);
+        return nullptr;
+    }
+    return a;
+}
+void be_aux_destroy(void* aux) {
+    FactorAux* a = (FactorAux*)aux;
+    if (!a) return;
+    if (a->side) cudaStreamDestroy(a->side);
+    if (a->ev_cols) cudaEventDestroy(a->ev_cols);
+    if (a->ev_panel) cudaEventDestroy(a->ev_panel);
+    delete a;
+}
+
+// factor the block columns [K0, K1) of one outer panel (left-looking inside the panel); all of A's columns [K0, K1)
+// must carry the trailing updates of the earlier panels
+static void factor_panel(cudaStream_t s, int B, int n, int bw, double* Kd, FgmresState* state, int K0, int K1) {
+    const size_t strideA = (size_t)n * n;
+    for (int k0 = K0; k0 < K1; k0 += kInner) {
+        const int nb = k0 + kInner < K1 ? kInner : K1 - k0;
+        const long long lim = (long long)k0 + nb + bw;
+        const int r1 = lim < n ? (int)lim : n;
+        // bring block column k0 up to date with the panel columns factored so far (depth k0 - K0) just before it is
+        // factored -- every block column is read-modify-written once instead of once per earlier inner block
+        launch_syrk(s, B, n, Kd, k0, r1, k0, k0 + nb, K0, k0, bw);
+        k_chol_diag<<<B, 256, 0, s>>>(n, Kd, strideA, k0, nb, state);
+        PDEOP_COUNT(1);
+        if (k0 + nb < r1) {
+            k_chol_trsm<<<dim3(cdiv(r1 - k0 - nb, 128), B), 128, 0, s>>>(n, Kd, strideA, k0, nb, r1);
+            PDEOP_COUNT(1);
+        }
+    }
+}
+
+void be_cholesky(stream_t st, int B, int n, int bw, double* Kd, double* Linv, FgmresState* state, bool use_chain,
+                 void* aux) {
     cudaStream_t s = (cudaStream_t)st;
     if (n <= kSmallN) {
         const size_t smem = (size_t)n * (n + 1) * sizeof(double);
@@ -1885,27 +1936,38 @@ void be_cholesky(stream_t st, int B, int n, int bw, double* Kd, double* Linv, Fg
         return;
     }
     const size_t strideA = (size_t)n * n;
-    for (int K0 = 0; K0 < n; K0 += kOuter) {
-        const int K1 = K0 + kOuter < n ? K0 + kOuter : n;
-        for (int k0 = K0; k0 < K1; k0 += kInner) {
-            const int nb = k0 + kInner < K1 ? kInner : K1 - k0;
-            const long long lim = (long long)k0 + nb + bw;
+    FactorAux* fa = (FactorAux*)aux;
+    if (!fa || n <= 2 * kOuter) {
+        for (int K0 = 0; K0 < n; K0 += kOuter) {
+            const int K1 = K0 + kOuter < n ? K0 + kOuter : n;
+            factor_panel(s, B, n, bw, Kd, state, K0, K1);
+            // trailing matrix: columns [K1, K1+bw), depth kOuter
+            const long long lim = (long long)K1 + bw;
             const int r1 = lim < n ? (int)lim : n;
-            // left-looking inside the outer panel: bring block column k0 up to date with the panel columns
-            // factored so far (depth k0 - K0) just before it is factored -- every block column is read-modify-
-            // written once instead of once per earlier inner block
-            launch_syrk(s, B, n, Kd, k0, r1, k0, k0 + nb, K0, k0, bw);
-            k_chol_diag<<<B, 256, 0, s>>>(n, Kd, strideA, k0, nb, state);
-            PDEOP_COUNT(1);
-            if (k0 + nb < r1) {
-                k_chol_trsm<<<dim3(cdiv(r1 - k0 - nb, 128), B), 128, 0, s>>>(n, Kd, strideA, k0, nb, r1);
-                PDEOP_COUNT(1);
-            }
+            launch_syrk(s, B, n, Kd, K1, r1, K1, r1, K0, K1, bw);
         }
-        // trailing matrix: columns [K1, K1+bw), depth kOuter
-        const long long lim = (long long)K1 + bw;
-        const int r1 = lim < n ? (int)lim : n;
-        launch_syrk(s, B, n, Kd, K1, r1, K1, r1, K0, K1, bw);
+    } else {
+        // Look-ahead.  The trailing update of panel k is split by columns: (a) the columns of panel k+1, (b) the rest.
+        // Panel k+1 reads and writes columns [K1, K2) only, (b) writes columns >= K2 and reads panel k's columns: the two
+        // are independent, so panel k+1 (a chain of short latency-bound kernels on a few SMs) runs on the side stream
+        // while the main stream streams (b) through the tensor pipe.  (kOuter is a multiple of the tile size: the
+        // row range of (b) starts at K2, the tiles above the diagonal are never launched.)
+        factor_panel(s, B, n, bw, Kd, state, 0, kOuter < n ? kOuter : n);
+        for (int K0 = 0; K0 < n; K0 += kOuter) {
+            const int K1 = K0 + kOuter < n ? K0 + kOuter : n;
+            if (K1 >= n) break;
+            const int K2 = K1 + kOuter < n ? K1 + kOuter : n;
+            const long long lim = (long long)K1 + bw;
+            const int r1 = lim < n ? (int)lim : n;
+            const int ca = K2 < r1 ? K2 : r1;
+            launch_syrk(s, B, n, Kd, K1, r1, K1, ca, K0, K1, bw);             // (a)
+            note(cudaEventRecord(fa->ev_cols, s));
+            note(cudaStreamWaitEvent(fa->side, fa->ev_cols, 0));
+            factor_panel(fa->side, B, n, bw, Kd, state, K1, K2);              // panel k+1
+            note(cudaEventRecord(fa->ev_panel, fa->side));
+            if (ca < r1) launch_syrk(s, B, n, Kd, ca, r1, ca, r1, K0, K1, bw);   // (b)
+            note(cudaStreamWaitEvent(s, fa->ev_panel, 0));
+        }
     }
     const int nblk = (n + kSolveBlk - 1) / kSolveBlk;
     k_trtri<<<dim3(nblk, B), kSolveBlk, 0, s>>>(n, Kd, strideA, Linv, nblk);

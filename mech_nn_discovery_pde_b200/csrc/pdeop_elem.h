@@ -33,7 +33,12 @@ struct LdL2 {
 // side, equation coefficients, reciprocal diagonals): keeps the L2 for the iterate, whose every value is gathered
 // 24 times within +-4 wavefront steps.  PDEOP_NO_STREAM_HINT disables it (A/B testing).
 PDEOP_HD double ld_stream(const double* p) {
-#if defined(__CUDA_ARCH__) && !defined(PDEOP_NO_STREAM_HINT)
+#if defined(__CUDA_ARCH__) && defined(PDEOP_STREAM_NOALLOC)
+    // A/B variant (tools/gs_bench.py, PDEOP_VARIANT_SO): no L1 allocation at all for the streams
+    double v;
+    asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+#elif defined(__CUDA_ARCH__) && !defined(PDEOP_NO_STREAM_HINT)
     return __ldcs(p);
 #else
     return *p;

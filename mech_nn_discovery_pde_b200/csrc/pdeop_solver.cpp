@@ -86,6 +86,7 @@ struct pdeop_plan {
     bool use_chain = true;
     int gs_pipe = 2;
     int device = -1;   // CUDA device the plan's tables live on; every entry point checks it is current
+    void* aux = nullptr;   // backend helper objects owned by the plan (side stream + events of the factorisation)
     ProfState prof;
 };
 
@@ -262,6 +263,7 @@ extern "C" int pdeop_plan_create_ex(int d, const int* dims, int order, int batch
     pl->off_Linv = poff;
     poff += be_chol_linv_doubles(batch, pl->nc, Lc.bw, pl->use_chain);   // inverse diagonal blocks (+ transposes, + scaled band)
     pl->persist_doubles = poff;
+    pl->aux = be_aux_create();
     if (check_backend()) {   // a failed table allocation or upload
         pdeop_plan_destroy(pl);
         return 1;
@@ -274,6 +276,7 @@ extern "C" void pdeop_plan_destroy(pdeop_plan* pl) {
     if (!pl) return;
     for (auto& lh : pl->lev)
         for (void* p : lh.owned) be_free(p);
+    if (pl->aux) be_aux_destroy(pl->aux);
     delete pl;
 }
 
@@ -449,7 +452,8 @@ static void setup_operator(pdeop_plan* pl, const double* coeffs, const double* c
         be_dense(st, pl->lev[lc].dev, B, P_T(pl, persist, lc), P_coef(pl, persist, lc), Kd);
     }
     ProfScope pf(pl->prof, PC_FACTOR, st);
-    be_cholesky(st, B, pl->nc, pl->lev[pl->n_grid - 1].dev.bw, P_Kd(pl, persist, sc), P_Linv(pl, persist), sc.state, pl->use_chain);
+    be_cholesky(st, B, pl->nc, pl->lev[pl->n_grid - 1].dev.bw, P_Kd(pl, persist, sc), P_Linv(pl, persist), sc.state, pl->use_chain,
+                pl->aux);
 }
 
 static void vcycle(pdeop_plan* pl, const pdeop_solver_cfg* cfg, void* persist, Scratch& sc, int l, const double* b,

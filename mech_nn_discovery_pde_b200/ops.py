@@ -154,7 +154,7 @@ def knobs_of(config, back):
             int(config.mg_fgmres_restarts_backward if back else config.mg_fgmres_restarts_forward),
             int(getattr(config, "gs_variant", 0)),
             mode, int(getattr(config, "mg_pcg_max_iter", 1000)), smoother, int(getattr(config, "mg_smoother_sweeps", 8)),
-            int(getattr(config, "mg_power_iters", 12))]
+            int(getattr(config, "mg_power_iters", 60))]
 
 
 def fparams_of(config):

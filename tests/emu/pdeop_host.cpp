@@ -371,7 +371,9 @@ void be_dense(stream_t, const LevelDev& L, int B, const double* T, const double*
         }
 }
 
-void be_cholesky(stream_t, int B, int n, int, double* Kd, double*, FgmresState* state, bool) {
+void* be_aux_create() { return nullptr; }
+void be_aux_destroy(void*) {}
+void be_cholesky(stream_t, int B, int n, int, double* Kd, double*, FgmresState* state, bool, void*) {
     for (int ib = 0; ib < B; ++ib) {
         double* A = Kd + (size_t)ib * n * n;
         for (int j = 0; j < n; ++j) {

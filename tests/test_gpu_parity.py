@@ -297,8 +297,8 @@ def test_1d_multigrid_vs_oracle(lib):
 
 
 def test_kamani_sized_dense_batch(lib):
-    """BASELINE config 2 shape: (24,) time grid, dense path, batch 4096; a slice of the batch is checked against
-    the oracle (instances are independent on the dense path), the rest for finiteness and residual."""
+    """BASELINE config 2 shape: (24,) time grid, dense path, batch 4096; a strided sample of the batch is checked
+    against the oracle instance by instance (instances are independent on the dense path), the rest for finiteness."""
     from mech_nn_discovery_pde_b200 import PDEDenseLayer
     dims, B = (24,), 4096
     iv = IV_LISTS["kamani"]
@@ -311,11 +311,16 @@ def test_kamani_sized_dense_batch(lib):
     u0, u, _ = layer(coeffs, t(inp["rhs"]), t(inp["iv_rhs"]), [t(s) for s in inp["steps"]])
     (u * t(inp["loss_w"]).reshape(u.shape)).sum().backward()
     assert torch.isfinite(u).all() and torch.isfinite(coeffs.grad).all()
-    k = 8
-    ref = O.dense_layer(dims, iv, inp["coeffs"][:k], inp["rhs"][:k], inp["iv_rhs"][:k], [s[:k] for s in inp["steps"]],
-                        grad_out=inp["loss_w"][:k].reshape(k, -1))
-    assert rel(u.detach().cpu().numpy()[:k].reshape(k, -1), ref.x) < 1e-8
-    assert rel(coeffs.grad.cpu().numpy()[:k], ref.d_coeffs) < 2e-7
+    # every 37th instance (111 of them: all residues of the warp- and CTA-sized groups the small-n kernels form)
+    idx = np.arange(0, B, 37)
+    k = len(idx)
+    ref = O.dense_layer(dims, iv, inp["coeffs"][idx], inp["rhs"][idx], inp["iv_rhs"][idx], [s[idx] for s in inp["steps"]],
+                        grad_out=inp["loss_w"][idx].reshape(k, -1))
+    x = u.detach().cpu().numpy().reshape(B, -1)[idx]
+    gc = coeffs.grad.cpu().numpy()[idx]
+    for i in range(k):      # per instance: one bad instance is not hidden in a batch norm
+        assert rel(x[i], ref.x[i]) < 1e-8
+        assert rel(gc[i], ref.d_coeffs[i]) < 2e-7
 
 
 def test_burgers_shaped_grid_properties(lib):
@@ -542,7 +547,7 @@ def test_fp32_storage_mode(lib):
 
 
 @pytest.mark.parametrize("case", [((16, 16), "burgers", 2, True, "chebyshev"), ((16, 16), "burgers", 2, True, "jacobi"),
-                                  ((8, 16, 16), "gl", 2, False, "chebyshev")])
+                                  ((16, 16, 16), "gl", 2, True, "chebyshev")])
 def test_converged_mode_vs_exact_solution(lib, case):
     """Converged mode (per-instance PCG, symmetric V-cycle with Chebyshev / weighted-Jacobi smoother, R = P^T): every
     instance reaches its relative tolerance, and solution and gradients equal the exact least-squares solution."""

@@ -20,7 +20,7 @@ modes = [int(a) for a in sys.argv[1 + nd:]] or [0, 4]
 B = int(os.environ.get("B", "32"))
 reps = int(os.environ.get("REPS", "10"))
 n_grid = int(os.environ.get("NGRID", "2"))
-lib = _lib.get_library()
+lib = _lib.PdeopLibrary(os.environ['PDEOP_VARIANT_SO']) if os.environ.get('PDEOP_VARIANT_SO') else _lib.get_library()
 G = int(np.prod(dims))
 M = 1 + 2 * nd
 g = torch.Generator().manual_seed(1)
