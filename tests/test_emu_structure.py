@@ -283,7 +283,7 @@ def test_surface_order1_and_n_ind_dim(name):
     run_surface_case(emu_library(), "cpu", name)
 
 
-def _converged_case(lib, device, dims, iv_name, B, n_grid, dsf, smoother, seed=123):
+def _converged_case(lib, device, dims, iv_name, B, n_grid, dsf, smoother, seed=123, max_iter=2500):
     """Converged mode (per-instance PCG, symmetric V-cycle) against the EXACT least-squares solution: the dense
     layer's Cholesky solve of the same system (semantics of solver/cg.py:51-147)."""
     import torch
@@ -294,7 +294,7 @@ def _converged_case(lib, device, dims, iv_name, B, n_grid, dsf, smoother, seed=1
     class Cfg(PDEConfig):
         solver_mode = "converged"
         mg_pcg_rtol = 1e-8
-        mg_pcg_max_iter = 2500
+        mg_pcg_max_iter = max_iter
         mg_smoother = smoother
         mg_smoother_sweeps = 8
 

@@ -547,10 +547,12 @@ def test_fp32_storage_mode(lib):
 
 
 @pytest.mark.parametrize("case", [((16, 16), "burgers", 2, True, "chebyshev"), ((16, 16), "burgers", 2, True, "jacobi"),
-                                  ((16, 16, 16), "gl", 2, True, "chebyshev")])
+                                  ((8, 16, 16), "gl", 2, False, "chebyshev")])
 def test_converged_mode_vs_exact_solution(lib, case):
     """Converged mode (per-instance PCG, symmetric V-cycle with Chebyshev / weighted-Jacobi smoother, R = P^T): every
     instance reaches its relative tolerance, and solution and gradients equal the exact least-squares solution."""
     from tests.test_emu_structure import _converged_case
     dims, ivn, n_grid, dsf, smoother = case
-    _converged_case(lib, "cuda:0", dims, ivn, 3, n_grid, dsf, smoother)
+    # the 3-D case needs ~3700 iterations (cond(K) ~ 1e10, rediscretised coarse operator); the exact reference solve on
+    # the CPU (n = 14 336 per instance) is what takes the time of this test, which is why the grid is not larger
+    _converged_case(lib, "cuda:0", dims, ivn, 3, n_grid, dsf, smoother, max_iter=2500 if len(dims) == 2 else 6000)
