@@ -350,11 +350,16 @@ def _mg_setup_context(ctx, inputs, output):
     coeffs, rhs, iv_rhs, cv, fv, bv, plan, knobs, knobs_bwd, fparams, flags = inputs
     x, persist, info = output
     ctx.plan, ctx.knobs_bwd, ctx.fparams, ctx.flags, ctx.n_levels = plan, list(knobs_bwd), list(fparams), flags, len(cv)
+    # `persist` (15-32 GB at the Ginzburg-Landau sizes) and `info` are outputs only so that the graph owns them: without
+    # this autograd would materialise a zero gradient of the same size for each of them in every backward
+    ctx.set_materialize_grads(False)
     ctx.save_for_backward(rhs, cv[0], fv[0], bv[0], x, persist, info)
 
 
 def _mg_backward(ctx, grad_x, grad_persist, grad_info):
     rhs, cv0, fv0, bv0, x, persist, info = ctx.saved_tensors
+    if grad_x is None:
+        grad_x = torch.zeros_like(x)
     if ctx.flags & FLAG_CHECK_SPD:
         _raise_if_not_spd(info)   # lazily: the forward never synchronises the host (cholesky_ex check, multigrid.py:439)
     d_coeffs, d_rhs, d_iv, d_cv, d_fv, d_bv, info_b = torch.ops.pdeop.mg_solve_backward(
@@ -373,11 +378,14 @@ def _dense_setup_context(ctx, inputs, output):
     coeffs, rhs, iv_rhs, cv, fv, bv, plan, flags = inputs
     x, persist, info = output
     ctx.plan, ctx.flags = plan, flags
+    ctx.set_materialize_grads(False)    # see _mg_setup_context
     ctx.save_for_backward(rhs, cv, fv, bv, x, persist, info)
 
 
 def _dense_backward(ctx, grad_x, grad_persist, grad_info):
     rhs, cv, fv, bv, x, persist, info = ctx.saved_tensors
+    if grad_x is None:
+        grad_x = torch.zeros_like(x)
     if ctx.flags & FLAG_CHECK_SPD:
         _raise_if_not_spd(info)
     d_coeffs, d_rhs, d_iv, d_cv, d_fv, d_bv, info_b = torch.ops.pdeop.dense_solve_backward(
