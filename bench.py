@@ -237,7 +237,7 @@ def run_ours(args, wl):
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: one JSON line only
+        # (NCCL_DEBUG is left alone: at WARN and above NCCL prints its version banner on stdout, next to the JSON line)
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch or wl["batch"]
     dims = wl["dims"]

@@ -94,3 +94,56 @@ def test_two_rank_shards_match_single_process():
                        [shard_batch(t(s), r, world) for s in inp["steps"]], theta)
         assert np.array_equal(u.numpy(), res[r][0])
         assert np.array_equal(theta.grad.numpy(), res[r][1])
+
+
+def _overlap_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mech_nn_discovery_pde_b200.parallel import OverlappedGradReducer, allreduce_param_grads
+    torch.manual_seed(5)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.Tanh(), torch.nn.Linear(16, 16), torch.nn.Tanh(),
+                              torch.nn.Linear(16, 3)).double()
+    unused = torch.nn.Parameter(torch.ones(4, dtype=torch.float64))     # never receives a gradient
+    params = list(net.parameters()) + [unused]
+    red = OverlappedGradReducer(params, bucket_bytes=1024)              # several buckets
+    out = []
+    for step in range(2):                                              # re-arming between steps
+        x = torch.randn(5, 6, dtype=torch.float64, generator=torch.Generator().manual_seed(100 * step + rank))
+        for p in params:
+            p.grad = None
+        (net(x) ** 2).sum().backward()
+        local = [p.grad.clone() if p.grad is not None else torch.zeros_like(p) for p in params]
+        red.finish()
+        overlapped = [p.grad.clone() for p in params]
+        for p, g in zip(params, local):                                # the one-bucket reference path on the same gradients
+            p.grad = g.clone()
+        allreduce_param_grads(params)
+        out.append(([g.numpy() for g in overlapped], [p.grad.numpy() for p in params], len(red.buckets)))
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_overlapped_grad_reducer_matches_flat_allreduce():
+    """Bucketed, hook-driven asynchronous all-reduce of the learned-parameter gradients equals the
+    single flat all-reduce, over two steps, with several buckets and a parameter that receives no gradient."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_overlap_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank in range(world):
+        for overlapped, flat, nb in res[rank]:
+            assert nb > 1
+            for a, b in zip(overlapped, flat):
+                assert np.array_equal(a, b)
+    for a, b in zip(res[0][1][0], res[1][1][0]):                       # both ranks hold the same sums
+        assert np.array_equal(a, b)
