@@ -2149,7 +2149,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t a, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t a) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
 }
-// bounded spin: a protocol error traps instead of hanging the GPU
+// bounded spin: a protocol error traps instead of hanging the GPU.  The bound is minutes of polling (each try_wait
+// suspends for a while before it returns false), not a latency budget: a slow co-tenant must not become a trap.
 __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
     for (long long spin = 0;; ++spin) {
         uint32_t ok;
@@ -2161,7 +2162,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
             : "r"(a), "r"(parity)
             : "memory");
         if (ok) return;
-        if (spin > (1LL << 22)) __trap();
+        if (spin > (1LL << 30)) __trap();
     }
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t a, uint32_t parity) {
@@ -2175,7 +2176,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t a, uint32_t parity) {
             : "r"(a), "r"(parity)
             : "memory");
         if (ok) return;
-        if (spin > (1LL << 22)) __trap();
+        if (spin > (1LL << 30)) __trap();
     }
 }
 // asynchronous 8-byte store into CTA `rank`'s shared memory (same offset as the local address) that completes

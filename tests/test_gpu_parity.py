@@ -387,7 +387,8 @@ def test_gs_kernel_variants_bit_identical(lib):
     canonical arithmetic: identical bits, on a level with one point per thread and step and on one with several
     rounds (register + global stash paths of the pipelined kernel); non-uniform steps exercise every table entry."""
     iv = IV_LISTS["gl"]
-    for dims, B, n_grid in (((8, 16, 16), 3, 2), ((32, 32, 32), 2, 3), ((16, 64, 32), 2, 3)):
+    # (32, 64, 64), n_grid 4: the benchmarked fine level -- the line kernel runs it as 4 CTAs per instance
+    for dims, B, n_grid in (((8, 16, 16), 3, 2), ((32, 32, 32), 2, 3), ((16, 64, 32), 2, 3), ((32, 64, 64), 2, 4)):
         G, M = int(np.prod(dims)), 7
         rng = np.random.default_rng(17)
         coeffs = np.zeros((B, G, M))
