@@ -335,7 +335,7 @@ def test_converged_mode_vs_exact_solution(smoother):
 
 # dims, iv list, batch, n_grid, downsample_first, sweeps, threads per CTA of the model (0: the kernel's 512)
 LINE_CASES = [
-    ((16, 16, 16), "gl", 2, 2, True, 5, 0),      # one CTA per instance
+    ((16, 16, 16), "gl", 1, 2, True, 5, 0),      # one CTA per instance
     ((16, 16, 16), "gl", 1, 2, True, 3, 64),     # four CTAs of four rows: progress counters, parked row
     ((12, 16, 16), "gl", 1, 2, False, 3, 96),    # two CTAs of six rows
     ((12, 16, 20), "gl", 1, 2, False, 1, 256),   # lines longer than rows, a single sweep, a CTA that is not full
@@ -350,7 +350,7 @@ def test_line_marching_gs_matches_sequential_sweeps(case):
     """The line-marching Gauss-Seidel kernel bodies (csrc/pdeop_gs_line.h) under the emulator's discrete-event model of
     the CUDA kernel -- random thread interleavings within what the split CTA barrier, the cp.async waits and the
     inter-CTA progress counters allow -- reproduce the sequential lexicographic sweeps bit for bit, for several random
-    schedules (solver/multigrid.py:399-405)."""
+    schedules (solver/multigrid.py:399-405); two random schedules per case."""
     import ctypes
     from oracle import pde_oracle as O
     from oracle.cases import make_inputs
@@ -369,7 +369,7 @@ def test_line_marching_gs_matches_sequential_sweeps(case):
     sr.plan.set_tuning("gs_pipe", 5)
     lib.dll.pdeop_emu_set_line_max_threads(ctypes.c_int(max_threads))
     try:
-        for seed in (1, 2, 3):
+        for seed in (1, 2):
             lib.dll.pdeop_emu_set_line_seed(ctypes.c_uint(seed))
             got = sr.stage(_lib.STAGE_GS, 0, b, x0, count=sweeps)
             assert lib.dll.pdeop_emu_line_last() == 1, "line kernel model not used, or it deadlocked"
