@@ -114,15 +114,19 @@ def test_seeded_stages_vs_reference(lib, name):
     assert rel_sampled(sr.stage(_lib.STAGE_VCYCLE, 0, v), s, "vcycle") < 1e-9
 
 
-@pytest.mark.parametrize("B", [1, 2])
-def test_benchmarked_config_vs_oracle(lib, B):
-    """bench.py's default workload itself -- Ginzburg-Landau 32x64x64, n_grid=4, downsample_first=False (coarsest
-    level 32x8x8, n = 14336: chain solver, pipelined GS on two levels), the benchmark's synthetic inputs and loss --
-    against fixtures from the pinned oracle port (oracle/make_golden_port.py; ~10 CPU-minutes per instance)."""
+PORT_CASES = [("gl32", 1), ("gl32", 2)] + ([("gl64", 1)] if os.path.exists(os.path.join(GOLDEN, "port_gl64_b1.npz")) else [])
+
+
+@pytest.mark.parametrize("wname,B", PORT_CASES)
+def test_benchmarked_config_vs_oracle(lib, wname, B):
+    """bench.py's workloads themselves -- gl32: Ginzburg-Landau 32x64x64, n_grid=4, downsample_first=False (coarsest
+    level 32x8x8, n = 14336: chain solver, staged GS kernel on two levels; BASELINE configuration 4); gl64: 64x128x128,
+    n_grid=4, downsample_first=True (the grid of BASELINE configuration 5) -- with the benchmark's synthetic inputs and
+    loss, against fixtures from the pinned oracle port (oracle/make_golden_port.py; ~10 / ~80 CPU-minutes per instance)."""
     import bench
     from mech_nn_discovery_pde_b200 import MultigridLayer
-    z = np.load(os.path.join(GOLDEN, f"port_gl32_b{B}.npz"))
-    wl = bench.WORKLOADS["gl32"]
+    z = np.load(os.path.join(GOLDEN, f"port_{wname}_b{B}.npz"))
+    wl = bench.WORKLOADS[wname]
     dev = torch.device("cuda:0")
     layer = MultigridLayer(bs=B, coord_dims=wl["dims"], order=2, n_ind_dim=1, n_iv=1, n_grid=wl["n_grid"],
                            downsample_first=wl["dsf"], init_index_mi_list=bench.IV_LISTS[wl["iv"]], n_iv_steps=1)
