@@ -11,7 +11,7 @@
 // one step earlier; a CTA owns `RPC` whole grid rows (i0), an instance spans C CTAs.
 //
 // Operands.  Nothing is re-gathered through per-point index tables:
-//   * u of the CTA's lines lives in a shared-memory RING [row][v mod 16][i1]: positions v-4 .. v+5 of every line,
+//   * u of the CTA's lines lives in a shared-memory RING [row][v mod 12][i1]: positions v-4 .. v+5 of every line,
 //     new values written by the owner when it finishes a point, old values fetched by the owner 7 positions ahead with
 //     cp.async (LDGSTS, no registers) -- all 24 u neighbours of a point along the three axes are plain shared-memory
 //     reads at [row+o][v][i1], [row][v][i1+o], [row][v+o][i1];
@@ -22,7 +22,9 @@
 //     end of an axis (one-sided stencils, lp_pde_central_diff.py:1000-1006): those values come from a small 16-slot
 //     ring of the four end lines of a row, from four registers (marching axis), or from two rows of global memory;
 //   * b, equation coefficients and reciprocal diagonals are streamed once per point (coalesced: consecutive i1 are
-//     consecutive in the wave layout) behind an L2 prefetch issued one step earlier.
+//     consecutive in the wave layout) behind an L2 prefetch issued one step earlier; the K tables and the rowbase
+//     columns of the rows a CTA reads are staged in shared memory once per call.
+// Measured slower than the hyperplane kernels on every level (profiles/r2_gs_experiments.md); opt-in (gs_pipe = 5).
 // A step is split as in the pipelined hyperplane kernel: A(n) finishes a point (the D backward distance-1 couplings,
 // which were written in step n-1, then the sequential channel solve), ARRIVE, B(n) gathers everything else for the
 // point of step n+1, WAIT.  The barrier is a CTA-wide split mbarrier; CTAs of an instance exchange rows through global
