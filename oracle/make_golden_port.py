@@ -7,7 +7,9 @@ reference on every smaller case, including the 3-D three-level downsample_first=
 oracle/make_golden_r2.py.  Inputs are bench.py's own synthetic inputs (same generator, same seed), so the test
 compares exactly what the benchmark runs.
 
-    python oracle/make_golden_port.py tests/golden gl32 1      # workload, batch
+    python oracle/make_golden_port.py tests/golden gl32 1      # workload, batch  (~10 CPU-minutes per instance)
+    python oracle/make_golden_port.py tests/golden gl64 1 487  # the grid of BASELINE configuration 5, sampling stride
+                                                               # (57 CPU-minutes, ~12 GB)
 
 Stored: FGMRES (iters, r_norm) forward and backward, norms and strided samples of u, d_coeffs, d_rhs, full
 d_iv_rhs and d_steps.
