@@ -168,9 +168,13 @@ class CoeffBuilder(torch.nn.Module):
         """fields: list of F tensors of one shape (B,G); w (NP,); exponents: 1-D tensor indexed by the ("abs", i)
         entries.  Returns coeffs (B,G,M), rhs (B,G) in fp64."""
         dev = fields[0].device
-        expo = self._expo_base.to(dev)
+        if self._expo_base.device != dev:      # once: the small index buffers follow the data (no per-call H2D copy)
+            self._expo_base = self._expo_base.to(dev)
+            self._expo_idx = self._expo_idx.to(dev)
+            self._expo_mask = self._expo_mask.to(dev)
+        expo = self._expo_base
         if exponents is not None:
-            expo = torch.where(self._expo_mask.to(dev), exponents.to(torch.float64)[self._expo_idx.to(dev)], expo)
+            expo = torch.where(self._expo_mask, exponents.to(torch.float64)[self._expo_idx], expo)
         return torch.ops.pdeop.coeff_build(list(fields), w, expo, self.spec, self.c0)
 
 

@@ -21,10 +21,15 @@ def _fd_weights(nodes):
     """
     sq = nodes * nodes
     vander = torch.stack([torch.ones_like(nodes), nodes, sq, sq * nodes, sq * sq], dim=-2)
-    target = nodes.new_zeros(5, 2)
-    target[1, 0] = 1.0
-    target[2, 1] = 2.0
-    return torch.linalg.solve(vander, target.expand(*vander.shape[:-2], 5, 2))
+    # right-hand sides e_1 and 2 e_2 (first and second derivative), built on the device without a host scalar copy
+    k = torch.arange(5, device=nodes.device)
+    target = torch.stack([(k == 1).to(nodes.dtype), 2.0 * (k == 2).to(nodes.dtype)], dim=-1)
+    rhs = target.expand(*vander.shape[:-2], 5, 2)
+    if vander.is_cuda and torch.cuda.is_current_stream_capturing():
+        # same LU kernels without the singularity check, which reads a status back to the host (not allowed while a
+        # CUDA graph is being captured; bench.py captures the dense workloads' whole step)
+        return torch.linalg.solve_ex(vander, rhs, check_errors=False)[0]
+    return torch.linalg.solve(vander, rhs)
 
 
 def central_line_values(steps, order=2):

@@ -561,3 +561,55 @@ def test_converged_mode_vs_exact_solution(lib, case):
     # the 3-D case needs ~3700 iterations (cond(K) ~ 1e10, rediscretised coarse operator); the exact reference solve on
     # the CPU (n = 14 336 per instance) is what takes the time of this test, which is why the grid is not larger
     _converged_case(lib, "cuda:0", dims, ivn, 3, n_grid, dsf, smoother, max_iter=2500 if len(dims) == 2 else 6000)
+
+
+def test_dense_layer_step_in_a_cuda_graph(lib):
+    """A whole dense-layer forward+backward (line values, solve, gradients) captured in a CUDA graph and replayed on new
+    inputs equals the eager call bit for bit: no host synchronisation or host-to-device copy hides in the path (the
+    Cholesky status check, which reads a value back, is the caller's to make after the replay), and every buffer the
+    library touches is a caller-owned tensor.  bench.py runs the host-launch-bound dense workloads this way."""
+    from mech_nn_discovery_pde_b200 import PDEConfig, PDEDenseLayer
+    dims, B = (24,), 64
+    iv = IV_LISTS["kamani"]
+    st = O.build_structure(dims, iv)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
+    layer = PDEDenseLayer(bs=B, coord_dims=dims, order=2, n_ind_dim=1, n_iv=1, init_index_mi_list=iv, n_iv_steps=1)
+
+    class NoSync(PDEConfig):
+        check_factorization = False
+    layer.config = NoSync
+    inp = make_inputs(dims, B, st.n_init, seed=5)
+    coeffs = t(inp["coeffs"]).requires_grad_(True)
+    rhs, ivr, steps, lw = t(inp["rhs"]), t(inp["iv_rhs"]), [t(s) for s in inp["steps"]], t(inp["loss_w"])
+
+    def step():
+        coeffs.grad = None
+        u0, u, _ = layer(coeffs, rhs, ivr, list(steps))
+        (u * lw.reshape(u.shape)).sum().backward()
+        return u
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        u_g = step()
+    grad_g = coeffs.grad
+    inp2 = make_inputs(dims, B, st.n_init, seed=6)          # new inputs into the tensors the graph reads
+    with torch.no_grad():
+        coeffs.copy_(t(inp2["coeffs"]))
+        rhs.copy_(t(inp2["rhs"]))
+        ivr.copy_(t(inp2["iv_rhs"]))
+    g.replay()
+    torch.cuda.synchronize()
+    u_replay, grad_replay = u_g.detach().clone(), grad_g.detach().clone()
+    layer.last_holder.check_factorization()
+    u_eager = step().detach()
+    assert torch.equal(u_replay, u_eager)
+    assert torch.equal(grad_replay, coeffs.grad)
+    ref = O.dense_layer(dims, iv, inp2["coeffs"], inp2["rhs"], inp2["iv_rhs"], inp["steps"])
+    assert rel(u_replay.cpu().numpy().reshape(B, -1), ref.x) < 1e-8
