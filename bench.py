@@ -15,7 +15,10 @@ The other BASELINE.json configurations are selectable with --workload: `kamani` 
 grid of the scaling configuration).
 
 Prints ONE JSON line (rank 0).  `value` is timed with the library's instrumentation OFF; the per-kernel-group
-breakdown and the roofline come from a second, separately timed pass with per-plan instrumentation on.
+breakdown and the roofline come from a second, separately timed pass with per-plan instrumentation on.  The step
+(everything but the collective) is captured in a CUDA graph and replayed (`--graph auto`; `cuda_graph` in the JSON
+line says whether it was): the dense workloads are host-launch bound, the multigrid ones gain ~2 %; the replay is
+checked against an eager step bit for bit before it is used.
 `--impl reference` times the reference's algorithm on the host CPU on a bounded sample: the oracle port for the
 workload itself and, when oracle/_ref (the unmodified reference + stub modules, built by oracle/make_ref.py) is
 present, the unmodified reference on its own default Ginzburg-Landau configuration as a cross-check.
@@ -237,8 +240,19 @@ def run_ours(args, wl):
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
-        # (NCCL_DEBUG is left alone: at WARN and above NCCL prints its version banner on stdout, next to the JSON line)
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator is created (NCCL_DEBUG at VERSION or above):
+        # stdout carries ONE JSON line, so file descriptor 1 points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     B = args.batch or wl["batch"]
     dims = wl["dims"]
     dense = bool(wl.get("dense"))
@@ -271,7 +285,7 @@ def run_ours(args, wl):
 
     builder = None if args.no_fused_builder else make_builder(wl)
 
-    def step(dv):
+    def local_step(dv):
         if theta.grad is not None:
             theta.grad = None
         if builder is not None:
@@ -282,9 +296,13 @@ def run_ours(args, wl):
         loss = (u0 * u0).sum()          # upstream gradient g = 2 u0
         loss.backward()
         pnet.grad[:theta.numel()] = theta.grad
+        return loss, u0
+
+    def step(dv):
+        out = local_step(dv)
         if world > 1:
             parallel.allreduce_param_grads([theta, pnet])   # the only collective: learned-parameter gradients
-        return loss, u0
+        return out
 
     resident = to_dev()
     torch.cuda.synchronize()
@@ -292,13 +310,15 @@ def run_ours(args, wl):
         step(resident)
     torch.cuda.synchronize()
 
-    # ---- CUDA graph of the whole step (dense workloads: ~100 short launches per step, host-launch bound) --------
-    # The captured step reads the static device tensors of `resident`; the e2e pass copies each step's host inputs into
-    # them.  The Cholesky status check moves out of the captured backward (it reads a value back) to after the replay.
+    # ---- CUDA graph of the step (everything but the collective).  The dense workloads (~100 short launches per step)
+    # are host-launch bound: 1.6-1.8x; the multigrid workloads gain ~2 %.  The captured step reads the static device
+    # tensors of `resident`; the e2e pass copies each step's host inputs into them.  The Cholesky status check moves out
+    # of the captured backward (it reads a value back) to after the replay.  `auto` leaves the 64x128x128 workload eager:
+    # a graph's private pool would hold a second 32 GB operator state next to the 100 GB of scratch.
     graph = None
     graph_launches = 0
-    want_graph = args.graph == "on" or (args.graph == "auto" and dense)
-    if want_graph and world == 1:
+    want_graph = args.graph == "on" or (args.graph == "auto" and args.workload != "gl64")
+    if want_graph:
         import warnings
         warnings.filterwarnings("ignore", message="The AccumulateGrad node's stream does not match")
         try:
@@ -310,15 +330,15 @@ def run_ours(args, wl):
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(3):
-                    eager_step(resident)
+                    local_step(resident)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             l0 = lib.launch_count()
             with torch.cuda.graph(g):
-                loss_g, u0_g = eager_step(resident)
+                loss_g, u0_g = local_step(resident)
             graph_launches = lib.launch_count() - l0
-            loss_eager = float(eager_step(resident)[0].item())
+            loss_eager = float(local_step(resident)[0].item())
             g.replay()
             torch.cuda.synchronize()
             layer.last_holder.check_factorization()
@@ -328,6 +348,8 @@ def run_ours(args, wl):
 
             def step(dv):       # noqa: F811  (dv must be `resident`: the graph reads those tensors)
                 graph.replay()
+                if world > 1:
+                    parallel.allreduce_param_grads([theta, pnet])
                 return loss_g, u0_g
         except Exception as e:   # noqa: BLE001
             import traceback
@@ -604,7 +626,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU (default: workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
-                    help="capture the whole step in a CUDA graph (auto: the dense workloads, which are host-launch bound)")
+                    help="capture the step in a CUDA graph (auto: every workload but gl64, whose state would not fit twice)")
     ap.add_argument("--cpu-budget", type=float, default=120.0)
     ap.add_argument("--no-fused-builder", action="store_true",
                     help="assemble coeffs with PyTorch ops instead of the fused coefficient-builder kernel")
