@@ -337,6 +337,8 @@ def run_ours(args, wl):
             l0 = lib.launch_count()
             with torch.cuda.graph(g):
                 loss_g, u0_g = local_step(resident)
+                if os.environ.get("PDEOP_BENCH_FORCE_GRAPH_FAIL"):      # test hook for the fallback path
+                    raise RuntimeError("forced capture failure")
             graph_launches = lib.launch_count() - l0
             loss_eager = float(local_step(resident)[0].item())
             g.replay()
@@ -359,6 +361,14 @@ def run_ours(args, wl):
             graph = None
             layer.config = PDEConfig
             step = eager_step
+            # leave nothing of the aborted capture behind: its private pool, half-built autograd state, stream state
+            g = loss_g = u0_g = None
+            theta.grad = None
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
+            for _ in range(max(args.warmup, 3)):
+                step(resident)
+            torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
